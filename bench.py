@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the gravity hot path on B200.
+
+Metric (BASELINE.json): direct-summation Ginteractions/s on config 2 — Hernquist halo N = 1e6,
+Plummer softening eps = 0.01, accelerations of all particles (reference call:
+Gravity(pos, mass, softening=0.01, kernel=KernelKind.Plummer).direct_accelerations(), i.e.
+direct.rs:443-524), fp32 interaction arithmetic checked against the float64 oracle.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 1000000] [--impl ours|reference]
+  torchrun --nproc-per-node N ... bench.py --gpus N ...     (one rank per GPU, targets sharded)
+
+One JSON line on stdout (rank 0). See DESIGN.md §Measurement for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "pynbody-extras_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+FLOP_PER_INTERACTION = 20.0  # GPU-Gems-3 convention for an acceleration interaction
+EPS = 0.01
+METRIC = "direct_sum_ginteractions_per_s"
+UNIT = "Ginteractions/s"
+
+
+def workload_config(n, n_gpus):
+    return {
+        "workload": f"Hernquist halo N={n} (a=1, r<=100a, seed 2), direct-sum accelerations, Plummer eps={EPS} "
+                    f"(BASELINE.json configs[1])",
+        "n_sources": n, "n_targets": n, "softening": EPS, "kernel": "Plummer", "want": "acc",
+        "sharding": f"targets/{n_gpus}" if n_gpus > 1 else "none",
+        "l2_policy": "inputs (40 MB f64 + 16 MB packed) are re-packed every step; each step streams "
+                     "the packed sources ~1000x from L2/HBM, kernel is FP32-pipe bound",
+    }
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(pos, mass, target_seconds=12.0):
+    """Time the CPU oracle (kind 'port': C++ restatement of direct.rs:587-658 with OpenMP on all host
+    cores; the Rust reference cannot be built in this image) on a bounded target sample of the same
+    workload. Returns (interactions/s, cores, sample description)."""
+    from oracle import oracle as O
+    n = pos.shape[0]
+    h = np.full(n, EPS)
+    cores = O.num_threads()
+    probe = max(cores * 2, 64)
+    t0 = time.perf_counter()
+    O.direct(pos, mass, h, targets=pos[:probe], kernel=0, want=2)
+    rate = probe * n / (time.perf_counter() - t0)
+    m = int(min(n, max(probe, rate * target_seconds / n)))
+    m = max(cores, m - m % cores)
+    if m < 512:  # keep the parallel (>= 512 targets) code path of the reference
+        m = 512
+    idx = np.linspace(0, n - 1, m).astype(np.int64)
+    t0 = time.perf_counter()
+    O.direct(pos, mass, h, targets=np.ascontiguousarray(pos[idx]), kernel=0, want=2)
+    dt = time.perf_counter() - t0
+    return m * n / dt, cores, f"{m} of {n} targets (evenly strided), all {n} sources, at-points kernel path, {dt:.1f} s"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from benchmarks.synthetic import hernquist
+    pos, mass = hernquist(args.n, seed=2)
+    rates = []
+    per_step = max(2.0, min(12.0, 60.0 / max(1, args.steps + args.warmup)))
+    sample = ""
+    cores = 1
+    for i in range(args.warmup + args.steps):
+        r, cores, sample = cpu_reference_rate(pos, mass, per_step)
+        if i >= args.warmup:
+            rates.append(r)
+    v = float(np.mean(rates)) / 1e9
+    n_int = args.n * (args.n - 1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": n_int / (v * 1e9) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.n, args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU oracle (C++/OpenMP port of direct.rs; Rust toolchain absent); ms_per_step extrapolated "
+                "from the sampled rate to the full N(N-1) interactions",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from benchmarks.synthetic import hernquist
+    from pynbodyext.gravity import Gravity, KernelKind
+    from pynbodyext.gravity import device as gdev
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n
+    pos, mass = hernquist(n, seed=2)
+
+    # ---- shards: rank r owns sources/targets [lo, hi); sources are replicated by one all-gather per step
+    bounds = [(n * r) // world for r in range(world + 1)]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    cnt = hi - lo
+    per = max(bounds[r + 1] - bounds[r] for r in range(world))
+    h_full = np.full(n, EPS)
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    if world > 1:
+        # padded equal-size shards packed as (x,y,z,m,h) rows so a single all_gather replicates everything
+        shard = np.zeros((per, 5))
+        shard[:cnt, 0:3] = pos[lo:hi]
+        shard[:cnt, 3] = mass[lo:hi]
+        shard[:cnt, 4] = EPS
+        d_shard = to_dev(shard)
+        d_all = torch.empty((world * per, 5), dtype=torch.float64, device=dev)
+    d_pos = to_dev(pos)
+    d_mass = to_dev(mass)
+    d_h = to_dev(h_full)
+
+    def gather_sources():
+        if world == 1:
+            return d_pos, d_mass, d_h
+        dist.all_gather_into_tensor(d_all, d_shard)
+        if per * world == n:
+            rows = d_all
+        else:
+            rows = torch.cat([d_all[r * per: r * per + (bounds[r + 1] - bounds[r])] for r in range(world)])
+        return rows[:, 0:3].contiguous(), rows[:, 3].contiguous(), rows[:, 4].contiguous()
+
+    kernel_ms = []
+
+    def step(record=False):
+        p, m_, h_ = gather_sources()
+        _, acc = gdev.direct_device(p, m_, h_, kernel=0, want=2, tgt_begin=lo, count=cnt, kernel_events=record)
+        return acc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = gdev.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record()
+    for _ in range(args.steps):
+        acc = step(record=True)
+        kernel_ms.append(None)  # filled after the sync (events are read without stalling the loop)
+    ev[1].record()
+    barrier()
+    ms_total = ev[0].elapsed_time(ev[1])
+    clocks = sampler.stop() if rank == 0 else None
+    launches = gdev.launch_count() - launches0
+    k_ms = gdev.last_kernel_ms()  # dominant kernel, last step (events on the launching stream)
+    t = torch.tensor([ms_total, k_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, k_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    n_int = float(n) * float(n - 1)
+    value = n_int / (ms_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (direct_kernel), per GPU
+    sm_max = peaks().get("sm_max_mhz", 1965.0)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    nominal_tf = sms * 128 * 2 * sm_max * 1e6 / 1e12
+    meas_tf = gdev.measure_fp32_peak(local, 0)
+    meas_tf2 = gdev.measure_fp32_peak(local, 1)
+    int_per_launch = float(cnt) * float(n - 1)
+    achieved_tf = FLOP_PER_INTERACTION * int_per_launch / (k_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "fp32", "kernel": "direct_kernel<acc,plummer_const,f32>", "achieved": achieved_tf,
+        "peak": meas_tf, "unit": "TFLOP/s", "frac": achieved_tf / meas_tf,
+        "peak_source": "measured here: FFMA-chain microbenchmark (pnbx_measure_fp32_peak), MEASURED_PEAKS.json has no FP32 entry",
+        "peak_nominal": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf, "peak_ffma2_chain": meas_tf2,
+        "flop_per_interaction": FLOP_PER_INTERACTION, "interactions_per_launch": int_per_launch,
+        "kernel_ms": k_ms, "ginteractions_per_s_kernel": int_per_launch / (k_ms * 1e-3) / 1e9,
+        "traffic": None,
+    }
+
+    # ---- parity in the same run: fp32 GPU vs float64 oracle on a 256-target subsample (rank 0)
+    parity = None
+    e2e = None
+    cpu = None
+    if rank == 0:
+        from oracle import oracle as O
+        idx = np.linspace(lo, hi - 1, 256).astype(np.int64)
+        a_gpu = acc[torch.from_numpy(idx - lo).to(dev)].cpu().numpy()
+        # oracle at-points includes the (exactly zero) self term for accelerations with eps > 0
+        _, a_ref = O.direct(pos, mass, h_full, targets=np.ascontiguousarray(pos[idx]), kernel=0, want=2)
+        parity = {"rms_rel_acc_vs_f64_oracle": float(np.sqrt((((a_gpu - a_ref) ** 2).sum(1) / (a_ref ** 2).sum(1)).mean())),
+                  "targets": 256, "tolerance": 1e-5}
+
+    # ---- e2e through the public drop-in API with pinned HOST buffers (H2D + D2H inside the timed region)
+    def pinned(a):
+        tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return tt.numpy()
+    pos_h, mass_h = pinned(pos), pinned(mass)
+    import pynbodyext._rust as backend
+
+    def e2e_step():
+        if world == 1:
+            g = Gravity(pos_h, mass_h, softening=EPS, kernel=KernelKind.Plummer)
+            return g.direct_accelerations()
+        from pynbodyext.gravity.sharded import direct_sharded
+        return direct_sharded(pos_h, mass_h, h_full, kernel=0, want=2, rank=rank, world=world, device=local)[1]
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e_steps = max(1, min(args.steps, 3))
+    for _ in range(e_steps):
+        out = e2e_step()
+    barrier()
+    e_dt = torch.tensor([(time.perf_counter() - t0) / e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
+    e2e = {"value": n_int / float(e_dt[0]) / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": int(pos.nbytes + mass.nbytes + h_full.nbytes) if world == 1 else int(cnt * 40),
+           "d2h_bytes_per_step": int(cnt * 24), "ms_per_step": float(e_dt[0]) * 1e3, "steps": e_steps,
+           "api": "Gravity(...).direct_accelerations() with pinned host numpy arrays" if world == 1
+                  else "pynbodyext.gravity.sharded.direct_sharded (per-rank shard H2D, NCCL all-gather, D2H)"}
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r, cores, sample = cpu_reference_rate(pos, mass, 12.0)
+        cpu = {"value": r / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(n, world), "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
+            "tflops_20flop": FLOP_PER_INTERACTION * value * 1e9 / 1e12,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

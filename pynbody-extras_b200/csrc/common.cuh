@@ -1,0 +1,182 @@
+// common.cuh — shared host-side plumbing of libpnbx_gravity.so (error state, device buffers,
+// stage timers, option handling). No CPU compute lives in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/pnbx_gravity.h"
+
+namespace pnbx {
+
+// ---- thread-local error + timing state (pnbx_last_error / pnbx_last_timings) ----
+std::string& last_error();
+struct StageTimes {
+    std::vector<std::pair<const char*, double>> v;
+};
+StageTimes& last_times();
+bool timing_enabled();  // GRAVITY_TIMING env var, same rule as tree.rs:5-16
+
+int fail(int code, const std::string& msg);
+
+struct CudaError {
+    cudaError_t e;
+    const char* what;
+    const char* file;
+    int line;
+};
+
+#define PNBX_CUDA(expr)                                                             \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) throw ::pnbx::CudaError{_e, #expr, __FILE__, __LINE__}; \
+    } while (0)
+
+struct ArgError {
+    int code;
+    std::string msg;
+};
+
+// Run `body`, translating exceptions into status codes + last_error().
+template <class F>
+int guarded(F&& body) {
+    try {
+        last_error().clear();
+        body();
+        return PNBX_OK;
+    } catch (const CudaError& ce) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)ce.e, cudaGetErrorString(ce.e),
+                 ce.file, ce.line, ce.what);
+        cudaGetLastError();  // clear sticky-less errors
+        return fail(PNBX_ERR_CUDA, buf);
+    } catch (const ArgError& ae) {
+        return fail(ae.code, ae.msg);
+    } catch (const std::exception& ex) {
+        return fail(PNBX_ERR_CUDA, ex.what());
+    }
+}
+
+// ---- execution context derived from pnbx_opts ----
+struct Exec {
+    int device = 0;
+    bool device_ptrs = false;
+    bool f64 = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool kernel_events = false;
+};
+Exec make_exec(const pnbx_opts* opts);  // selects the device; throws if none
+void finish_exec(Exec& ex);             // sync (host mode) + release
+
+// Stream-ordered device buffer (cudaMallocAsync pool: no per-call cudaMalloc cost after warm-up).
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(size_t count, cudaStream_t stream) { alloc(count, stream); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p; n = o.n; s = o.s;
+            o.p = nullptr; o.n = 0;
+        }
+        return *this;
+    }
+    void alloc(size_t count, cudaStream_t stream) {
+        release();
+        s = stream;
+        n = count;
+        if (count) PNBX_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), stream));
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    T* get() const { return p; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// Input array that may live on the host (copied in, like gravity.rs:154-180) or on the device.
+template <class T>
+struct InArray {
+    const T* d = nullptr;
+    DevBuf<T> owned;
+    void bind(const T* src, size_t count, const Exec& ex) {
+        if (!src || count == 0) { d = nullptr; return; }
+        if (ex.device_ptrs) { d = src; return; }
+        owned.alloc(count, ex.stream);
+        PNBX_CUDA(cudaMemcpyAsync(owned.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ex.stream));
+        d = owned.p;
+    }
+};
+
+// Output array: device pointer given by the caller, or a temp that is copied back to the host.
+template <class T>
+struct OutArray {
+    T* d = nullptr;
+    T* host = nullptr;
+    size_t n = 0;
+    DevBuf<T> owned;
+    void bind(T* dst, size_t count, const Exec& ex) {
+        n = count;
+        if (!dst || count == 0) { d = nullptr; return; }
+        if (ex.device_ptrs) { d = dst; return; }
+        owned.alloc(count, ex.stream);
+        d = owned.p;
+        host = dst;
+    }
+    void finish(const Exec& ex) {
+        if (host && n) PNBX_CUDA(cudaMemcpyAsync(host, d, n * sizeof(T), cudaMemcpyDeviceToHost, ex.stream));
+    }
+};
+
+// CUDA-event stage timer; records into last_times() when GRAVITY_TIMING is set.
+struct StageTimer {
+    cudaStream_t s;
+    bool on;
+    cudaEvent_t a = nullptr, b = nullptr;
+    const char* label = nullptr;
+    explicit StageTimer(cudaStream_t stream);
+    ~StageTimer();
+    void begin(const char* l);
+    void end();
+};
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Every kernel launch of this library goes through PNBX_LAUNCH so bench.py can report `gpu_launches`.
+int64_t& launch_counter();
+#define PNBX_LAUNCH(kernel, grid, block, smem, stream, ...)          \
+    do {                                                             \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+        ++::pnbx::launch_counter();                                  \
+    } while (0)
+
+// CUDA events around the dominant kernel of the last call (no sync inside the call): recorded on the
+// call's stream when pnbx_opts.flags has PNBX_FLAG_KERNEL_EVENTS; read back by pnbx_last_kernel_ms().
+struct KernelEvents {
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool armed = false, valid = false;
+    void begin(cudaStream_t s);
+    void end(cudaStream_t s);
+};
+KernelEvents& kernel_events();
+
+// Shared by direct.cu and tree.cu: float64 bounding box of (n,3) positions on the device.
+// out6 = {minx,miny,minz,maxx,maxy,maxz} (device). Follows tree.rs:628-640.
+void launch_bbox(const double* pos, int64_t n, double* out6, cudaStream_t s);
+
+}  // namespace pnbx

@@ -1,0 +1,501 @@
+// direct.cu — K1: direct-summation potential / acceleration on B200 (sm_100a).
+//
+// Reproduces the eight solvers of the reference's direct.rs:115-658 (Newtonian and
+// Plummer / cubic-spline softened, self and at-points) behind pnbx_direct().
+//
+// Design: the pairwise sum is FP32-FMA-pipe bound, not a contraction, so no
+// tensor cores. Sources are packed once to float4 (x,y,z,m) relative to the bounding-box
+// centre (float64 subtraction before the cast), streamed through shared memory by TMA bulk
+// copies (cp.async.bulk + mbarrier, 3 stages) and broadcast to a register-blocked loop of
+// TPT targets per thread. FP32 partial sums are folded into float64 accumulators once per
+// 512-source tile, so no accumulator ever absorbs more than 512 terms (fp32 accuracy).
+// The source range is split over blockIdx.y so the grid holds >= ~20 waves of work items; split
+// partials are combined in a fixed order (deterministic, no float atomics).
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace pnbx {
+namespace {
+
+constexpr int DT = 256;     // threads per block
+constexpr int TPT = 4;      // targets per thread
+constexpr int STAGES = 3;   // smem pipeline depth
+constexpr int TILE32 = 512; // sources per stage, fp32 path (8 KB of float4)
+constexpr int TILE64 = 256; // sources per stage, fp64 verification path (8 KB of double4)
+
+enum Soft { SOFT_NEWTON = 0, SOFT_PLUMMER_CONST = 1, SOFT_PLUMMER_PAIR = 2, SOFT_SPLINE = 3 };
+
+template <class T>
+struct alignas(sizeof(T) * 4) Vec4 {
+    T x, y, z, w;
+};
+
+// ------------------------------------------------------------------ mbarrier / TMA bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (UBLKCP in SASS).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // one MUFU.RSQ
+    return y;
+}
+__device__ __forceinline__ double rsqrt_fast(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ float tmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double tmax(double a, double b) { return fmax(a, b); }
+template <class T>
+__device__ __forceinline__ T tiny();
+template <>
+__device__ __forceinline__ float tiny<float>() { return FLT_MIN; }
+template <>
+__device__ __forceinline__ double tiny<double>() { return DBL_MIN; }  // R2_TINY, direct.rs:7
+
+// Springel W2 kernel and derivative (kernel.rs:84-128), evaluated only for r < h.
+template <class T>
+__device__ __forceinline__ T w2_inner(T u) {
+    T u2 = u * u;
+    if (u < T(0.5)) return T(16.0 / 3.0) * u2 + u2 * u2 * (T(32.0 / 5.0) * u - T(48.0 / 5.0)) - T(14.0 / 5.0);
+    return T(1.0 / 15.0) / u + u2 * (T(32.0 / 3.0) + u * (T(-16.0) + u * (T(48.0 / 5.0) - T(32.0 / 15.0) * u))) -
+           T(16.0 / 5.0);
+}
+template <class T>
+__device__ __forceinline__ T w2p_inner(T u) {
+    T u2 = u * u;
+    if (u < T(0.5)) return u * (T(32.0 / 3.0) + u2 * (T(32.0) * u - T(192.0 / 5.0)));
+    return T(-1.0 / 15.0) / u2 + u * (T(64.0 / 3.0) + u * (T(-48.0) + u * (T(192.0 / 5.0) - T(32.0 / 3.0) * u)));
+}
+
+// One target-source interaction. s = (dx-able source xyz, mass); hj = source softening.
+// e = per-target constant: eps^2 (+tiny) for NEWTON / PLUMMER_CONST, h_i for the pair modes.
+template <int WANT, int SOFT, bool CHECK, class T>
+__device__ __forceinline__ void interact(T xi, T yi, T zi, T e, const Vec4<T>& s, T hj, bool is_self, T& ax, T& ay,
+                                         T& az, T& pot) {
+    T dx = s.x - xi, dy = s.y - yi, dz = s.z - zi;
+    T m = s.w;
+    if (SOFT == SOFT_NEWTON || SOFT == SOFT_PLUMMER_CONST || SOFT == SOFT_PLUMMER_PAIR) {
+        T r2;
+        if (SOFT == SOFT_PLUMMER_PAIR) {
+            T h = tmax(e, hj);  // direct.rs:402,426,475,506 (self) / :560,577,623,646 (points: e = 0)
+            r2 = fma(h, h, tiny<T>());
+        } else {
+            r2 = e;
+        }
+        r2 = fma(dx, dx, r2);
+        r2 = fma(dy, dy, r2);
+        r2 = fma(dz, dz, r2);
+        if (CHECK && is_self) {  // own particle (index match): contributes exactly nothing
+            r2 = T(1);
+            m = T(0);
+        }
+        T rinv = rsqrt_fast(r2);
+        if (WANT == PNBX_WANT_POT) pot = fma(-m, rinv, pot);
+        if (WANT & PNBX_WANT_ACC) {
+            T mr = m * rinv;
+            if (WANT & PNBX_WANT_POT) pot -= mr;
+            T g = mr * (rinv * rinv);
+            ax = fma(dx, g, ax);
+            ay = fma(dy, g, ay);
+            az = fma(dz, g, az);
+        }
+    } else {  // SOFT_SPLINE
+        T h = tmax(e, hj);
+        T r2 = fma(dx, dx, tiny<T>());
+        r2 = fma(dy, dy, r2);
+        r2 = fma(dz, dz, r2);
+        if (CHECK && is_self) {
+            r2 = T(1);
+            m = T(0);
+        }
+        T rinv = rsqrt_fast(r2);
+        T k = -rinv;                   // potential per unit mass
+        T g = rinv * rinv * rinv;      // accel factor
+        if (h > T(0) && r2 < h * h) {  // kernel.rs:46-54, 72-80
+            T hinv = T(1) / h;
+            T u = (r2 * rinv) * hinv;
+            if (WANT & PNBX_WANT_POT) k = w2_inner(u) * hinv;
+            if (WANT & PNBX_WANT_ACC) g = w2p_inner(u) * (hinv * hinv) * rinv;
+        }
+        if (WANT & PNBX_WANT_POT) pot = fma(m, k, pot);
+        if (WANT & PNBX_WANT_ACC) {
+            T mg = m * g;
+            ax = fma(dx, mg, ax);
+            ay = fma(dy, mg, ay);
+            az = fma(dz, mg, az);
+        }
+    }
+}
+
+template <int WANT, int SOFT, class T, int TILE>
+__global__ void __launch_bounds__(DT, 2)
+direct_kernel(const Vec4<T>* __restrict__ src, const T* __restrict__ src_h, int64_t n_src,
+              const Vec4<T>* __restrict__ tgt, const T* __restrict__ tgt_h, int64_t m, int64_t self_base,
+              T eps2_const, int tiles_per_split, double* __restrict__ out_pot, double* __restrict__ out_acc) {
+    constexpr bool PAIR_H = (SOFT == SOFT_PLUMMER_PAIR || SOFT == SOFT_SPLINE);
+    __shared__ Vec4<T> s_src[STAGES][TILE];
+    __shared__ alignas(16) T s_h[PAIR_H ? STAGES : 1][PAIR_H ? TILE : 4];
+    __shared__ alignas(8) uint64_t s_full[STAGES];
+
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = (n_src + TILE - 1) / TILE;
+    const int64_t tile_begin = (int64_t)blockIdx.y * tiles_per_split;
+    const int64_t tile_end = tile_begin + tiles_per_split < n_tiles ? tile_begin + tiles_per_split : n_tiles;
+    const int64_t tgt_base = (int64_t)blockIdx.x * (DT * TPT);
+
+    // ---- targets in registers
+    T xi[TPT], yi[TPT], zi[TPT], ei[TPT];
+    int64_t gi[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+        int64_t i = tgt_base + k * DT + tid;
+        if (i > m - 1) i = m - 1;
+        Vec4<T> t = tgt[i];
+        xi[k] = t.x; yi[k] = t.y; zi[k] = t.z;
+        if (PAIR_H) ei[k] = tgt_h ? tgt_h[i] : T(0);
+        else ei[k] = eps2_const;
+        gi[k] = self_base >= 0 ? self_base + i : -1;
+    }
+    double Ax[TPT], Ay[TPT], Az[TPT], P[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) Ax[k] = Ay[k] = Az[k] = P[k] = 0.0;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t tile) {  // called by thread 0 only
+        int st = (int)((tile - tile_begin) % STAGES);
+        int64_t j0 = tile * TILE;
+        int cnt = (int)(n_src - j0 < TILE ? n_src - j0 : TILE);
+        uint32_t bytes = (uint32_t)cnt * sizeof(Vec4<T>);
+        uint32_t hbytes = PAIR_H ? (uint32_t)((cnt * sizeof(T) + 15) / 16 * 16) : 0u;  // src_h is padded
+        mbar_expect_tx(&s_full[st], bytes + hbytes);
+        bulk_g2s(&s_src[st][0], src + j0, bytes, &s_full[st]);
+        if (PAIR_H) bulk_g2s(&s_h[st][0], src_h + j0, hbytes, &s_full[st]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < STAGES - 1; ++s)
+            if (tile_begin + s < tile_end) issue(tile_begin + s);
+
+    const int64_t blk_lo = self_base >= 0 ? self_base + tgt_base : INT64_MAX;
+    const int64_t blk_hi = self_base >= 0 ? blk_lo + DT * TPT : INT64_MIN;
+
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+        const int it = (int)(tile - tile_begin);
+        const int st = it % STAGES;
+        if (tid == 0 && tile + STAGES - 1 < tile_end) issue(tile + STAGES - 1);
+        mbar_wait(&s_full[st], (uint32_t)((it / STAGES) & 1));
+
+        const int64_t j0 = tile * TILE;
+        const int cnt = (int)(n_src - j0 < TILE ? n_src - j0 : TILE);
+        T ax[TPT], ay[TPT], az[TPT], p[TPT];
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) ax[k] = ay[k] = az[k] = p[k] = T(0);
+
+        const bool diag = (j0 < blk_hi) && (j0 + cnt > blk_lo);  // tile holds some of this block's own particles
+        if (!diag && cnt == TILE) {
+#pragma unroll 8
+            for (int j = 0; j < TILE; ++j) {
+                Vec4<T> s = s_src[st][j];
+                T hj = PAIR_H ? s_h[st][j] : T(0);
+#pragma unroll
+                for (int k = 0; k < TPT; ++k) interact<WANT, SOFT, false, T>(xi[k], yi[k], zi[k], ei[k], s, hj, false, ax[k], ay[k], az[k], p[k]);
+            }
+        } else {
+            // ragged tail and/or self-skip by index (direct.rs:166, 297, 421, 501)
+            for (int j = 0; j < cnt; ++j) {
+                Vec4<T> s = s_src[st][j];
+                T hj = PAIR_H ? s_h[st][j] : T(0);
+                const int64_t gj = j0 + j;
+#pragma unroll
+                for (int k = 0; k < TPT; ++k)
+                    interact<WANT, SOFT, true, T>(xi[k], yi[k], zi[k], ei[k], s, hj, gj == gi[k], ax[k], ay[k], az[k], p[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) {  // fold the tile partials into float64
+            if (WANT & PNBX_WANT_ACC) { Ax[k] += (double)ax[k]; Ay[k] += (double)ay[k]; Az[k] += (double)az[k]; }
+            if (WANT & PNBX_WANT_POT) P[k] += (double)p[k];
+        }
+        __syncthreads();  // everyone is done with stage `st` before it is refilled
+    }
+
+    const int64_t split_off = (int64_t)blockIdx.y * m;
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+        int64_t i = tgt_base + k * DT + tid;
+        if (i < m) {
+            if (WANT & PNBX_WANT_POT) out_pot[split_off + i] = P[k];
+            if (WANT & PNBX_WANT_ACC) {
+                double* a = out_acc + 3 * (split_off + i);
+                a[0] = Ax[k]; a[1] = Ay[k]; a[2] = Az[k];
+            }
+        }
+    }
+}
+
+// Sum the per-split partials in split order (fixed order => run-to-run deterministic).
+__global__ void reduce_splits(const double* __restrict__ part, int64_t count, int splits, double* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double s = 0.0;
+    for (int k = 0; k < splits; ++k) s += part[(int64_t)k * count + i];
+    out[i] = s;
+}
+
+// float64 (n,3) positions [+ mass] -> Vec4<T>(x-cx, y-cy, z-cz, m|1|w0). centre read from device bbox.
+template <class T>
+__global__ void pack_points(const double* __restrict__ pos, const double* __restrict__ mass, int64_t n,
+                            const double* __restrict__ bbox6, T w_default, Vec4<T>* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double cx = (bbox6[0] + bbox6[3]) * 0.5, cy = (bbox6[1] + bbox6[4]) * 0.5, cz = (bbox6[2] + bbox6[5]) * 0.5;
+    Vec4<T> v;
+    v.x = (T)(pos[3 * i + 0] - cx);
+    v.y = (T)(pos[3 * i + 1] - cy);
+    v.z = (T)(pos[3 * i + 2] - cz);
+    v.w = mass ? (T)mass[i] : w_default;
+    out[i] = v;
+}
+template <class T>
+__global__ void pack_scalar(const double* __restrict__ in, int64_t n, int64_t n_padded, T* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_padded) return;
+    out[i] = i < n ? (T)in[i] : T(0);
+}
+// min / max of the softening array, to detect the (common) constant-softening case.
+__global__ void minmax_scalar_blocks(const double* __restrict__ in, int64_t n, double* __restrict__ part) {
+    __shared__ double smn[256], smx[256];
+    double mn = INFINITY, mx = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        double v = in[i];
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+    }
+    smn[threadIdx.x] = mn;
+    smx[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            smn[threadIdx.x] = fmin(smn[threadIdx.x], smn[threadIdx.x + o]);
+            smx[threadIdx.x] = fmax(smx[threadIdx.x], smx[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = smn[0]; part[2 * blockIdx.x + 1] = smx[0]; }
+}
+__global__ void minmax_pairs_final(const double* __restrict__ part, int nparts, double* __restrict__ out2) {
+    double mn = INFINITY, mx = -INFINITY;
+    for (int i = 0; i < nparts; ++i) { mn = fmin(mn, part[2 * i]); mx = fmax(mx, part[2 * i + 1]); }
+    out2[0] = mn;
+    out2[1] = mx;
+}
+
+template <int WANT, int SOFT, class T, int TILE>
+void launch_direct_t(const Vec4<T>* src, const T* src_h, int64_t n, const Vec4<T>* tgt, const T* tgt_h, int64_t m,
+                     int64_t self_base, T eps2, int splits, int tiles_per_split, double* pot, double* acc,
+                     cudaStream_t s) {
+    dim3 grid((unsigned)ceil_div(m, DT * TPT), (unsigned)splits);
+    PNBX_LAUNCH((direct_kernel<WANT, SOFT, T, TILE>), grid, DT, 0, s, src, src_h, n, tgt, tgt_h, m, self_base, eps2,
+                tiles_per_split, pot, acc);
+}
+
+template <class T, int TILE>
+void launch_direct(int want, int soft, const Vec4<T>* src, const T* src_h, int64_t n, const Vec4<T>* tgt,
+                   const T* tgt_h, int64_t m, int64_t self_base, T eps2, int splits, int tiles_per_split,
+                   double* pot, double* acc, cudaStream_t s) {
+#define PNBX_CASE(W, S)                                                                                          \
+    if (want == W && soft == S) {                                                                                \
+        launch_direct_t<W, S, T, TILE>(src, src_h, n, tgt, tgt_h, m, self_base, eps2, splits, tiles_per_split,  \
+                                       pot, acc, s);                                                             \
+        return;                                                                                                  \
+    }
+    PNBX_CASE(1, SOFT_NEWTON) PNBX_CASE(2, SOFT_NEWTON) PNBX_CASE(3, SOFT_NEWTON)
+    PNBX_CASE(1, SOFT_PLUMMER_CONST) PNBX_CASE(2, SOFT_PLUMMER_CONST) PNBX_CASE(3, SOFT_PLUMMER_CONST)
+    PNBX_CASE(1, SOFT_PLUMMER_PAIR) PNBX_CASE(2, SOFT_PLUMMER_PAIR) PNBX_CASE(3, SOFT_PLUMMER_PAIR)
+    PNBX_CASE(1, SOFT_SPLINE) PNBX_CASE(2, SOFT_SPLINE) PNBX_CASE(3, SOFT_SPLINE)
+#undef PNBX_CASE
+    throw ArgError{PNBX_ERR_ARG, "internal: no direct kernel variant"};
+}
+
+template <class T, int TILE>
+void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const double* d_h, int64_t n,
+                const double* d_tgt, int64_t m, int64_t tgt_begin, int kernel, int want, double* d_pot,
+                double* d_acc, StageTimer& tm) {
+    cudaStream_t s = ex.stream;
+    const bool self = d_tgt == nullptr;
+
+    tm.begin("direct.pack");
+    DevBuf<double> bbox(6, s);
+    launch_bbox(d_pos, n, bbox.get(), s);
+
+    // softening mode
+    int soft = SOFT_NEWTON;
+    T eps2 = sizeof(T) == 4 ? (T)FLT_MIN : (T)DBL_MIN;  // the reference's + R2_TINY
+    bool pair_h = false;
+    if (kernel == PNBX_KERNEL_PLUMMER || kernel == PNBX_KERNEL_SPLINE) {
+        double hmm[2] = {0.0, 0.0};
+        if (d_h) {
+            DevBuf<double> part(2 * 296, s), res(2, s);
+            PNBX_LAUNCH(minmax_scalar_blocks, 296, 256, 0, s, d_h, n, part.get());
+            PNBX_LAUNCH(minmax_pairs_final, 1, 1, 0, s, part.get(), 296, res.get());
+            PNBX_CUDA(cudaMemcpyAsync(hmm, res.get(), sizeof(hmm), cudaMemcpyDeviceToHost, s));
+            PNBX_CUDA(cudaStreamSynchronize(s));
+        }
+        const bool constant = hmm[0] == hmm[1];
+        if (kernel == PNBX_KERNEL_PLUMMER) {
+            // constant h: self max(h,h) = h; points max(h,0). Negative constant: |h| in self mode (h*h),
+            // Newtonian at points (direct.rs:560) — both equal h_eff^2 below.
+            if (constant) {
+                double he = self ? hmm[0] : std::max(hmm[0], 0.0);
+                soft = SOFT_PLUMMER_CONST;
+                eps2 = (T)(he * he) + eps2;
+            } else {
+                soft = SOFT_PLUMMER_PAIR;
+                pair_h = true;
+            }
+        } else {
+            if (constant && hmm[0] <= 0.0) soft = SOFT_NEWTON;  // spline with h<=0 is Newtonian (kernel.rs:46-48)
+            else { soft = SOFT_SPLINE; pair_h = true; }
+        }
+    }
+
+    DevBuf<Vec4<T>> src4((size_t)n, s);
+    {
+        int64_t blocks = ceil_div(n, 256);
+        PNBX_LAUNCH(pack_points<T>, (unsigned)blocks, 256, 0, s, d_pos, d_mass, n, bbox.get(), T(1), src4.get());
+    }
+    DevBuf<T> srch;
+    if (pair_h) {
+        int64_t np = ceil_div(n, 4) * 4 + 4;  // padded to 16 B granules for the bulk copy
+        srch.alloc((size_t)np, s);
+        PNBX_LAUNCH(pack_scalar<T>, (unsigned)ceil_div(np, 256), 256, 0, s, d_h, n, np, srch.get());
+    }
+    DevBuf<Vec4<T>> tgt4;
+    const Vec4<T>* tgt_ptr;
+    const T* tgt_h_ptr = nullptr;
+    if (self) {
+        tgt_ptr = src4.get() + tgt_begin;
+        if (pair_h) tgt_h_ptr = srch.get() + tgt_begin;
+    } else {
+        tgt4.alloc((size_t)m, s);
+        PNBX_LAUNCH(pack_points<T>, (unsigned)ceil_div(m, 256), 256, 0, s, d_tgt, nullptr, m, bbox.get(), T(0), tgt4.get());
+        tgt_ptr = tgt4.get();
+    }
+    PNBX_CUDA(cudaGetLastError());
+    tm.end();
+
+    // work decomposition: target blocks x source splits, >= ~20 waves of 2 CTAs/SM when possible
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ex.device);
+    const int64_t n_tb = ceil_div(m, DT * TPT);
+    const int64_t n_tiles = ceil_div(n, TILE);
+    int64_t splits = ceil_div((int64_t)sms * 2 * 20, n_tb);
+    splits = std::max<int64_t>(1, std::min<int64_t>(splits, std::min<int64_t>(64, ceil_div(n_tiles, 8))));
+    int tiles_per_split = (int)ceil_div(n_tiles, splits);
+    splits = ceil_div(n_tiles, tiles_per_split);
+
+    DevBuf<double> part_pot, part_acc;
+    double* kp = d_pot;
+    double* ka = d_acc;
+    if (splits > 1) {
+        if (want & PNBX_WANT_POT) { part_pot.alloc((size_t)(splits * m), s); kp = part_pot.get(); }
+        if (want & PNBX_WANT_ACC) { part_acc.alloc((size_t)(splits * m * 3), s); ka = part_acc.get(); }
+    }
+    tm.begin("direct.kernel");
+    kernel_events().begin(s);
+    launch_direct<T, TILE>(want, soft, src4.get(), srch.get(), n, tgt_ptr, tgt_h_ptr, m, self ? tgt_begin : -1, eps2,
+                           (int)splits, tiles_per_split, kp, ka, s);
+    kernel_events().end(s);
+    PNBX_CUDA(cudaGetLastError());
+    if (splits > 1) {
+        if (want & PNBX_WANT_POT)
+            PNBX_LAUNCH(reduce_splits, (unsigned)ceil_div(m, 256), 256, 0, s, kp, m, (int)splits, d_pot);
+        if (want & PNBX_WANT_ACC)
+            PNBX_LAUNCH(reduce_splits, (unsigned)ceil_div(3 * m, 256), 256, 0, s, ka, 3 * m, (int)splits, d_acc);
+        PNBX_CUDA(cudaGetLastError());
+    }
+    tm.end();
+}
+
+}  // namespace
+}  // namespace pnbx
+
+extern "C" int pnbx_direct(const double* src_pos, const double* src_mass, const double* src_h, int64_t n,
+                           const double* tgt_pos, int64_t m, int64_t tgt_begin, int kernel, int want,
+                           double* out_pot, double* out_acc, const pnbx_opts* opts) {
+    using namespace pnbx;
+    return guarded([&] {
+        if (n < 0 || m < 0) throw ArgError{PNBX_ERR_ARG, "negative size"};
+        if (n > 0 && !src_pos) throw ArgError{PNBX_ERR_ARG, "positions must be (N,3) float64 array"};
+        if (kernel != PNBX_KERNEL_NONE && kernel != PNBX_KERNEL_PLUMMER && kernel != PNBX_KERNEL_SPLINE)
+            throw ArgError{PNBX_ERR_ARG, "kernel must be 0 (Plummer) or 1 (CubicSplineW2)"};
+        if (kernel == PNBX_KERNEL_NONE && src_h)  // gravity.rs:480-484
+            throw ArgError{PNBX_ERR_ARG, "softenings require an explicit kernel; pass kernel=0/1 (or omit softenings)"};
+        if (!(want & (PNBX_WANT_POT | PNBX_WANT_ACC)) || (want & ~3)) throw ArgError{PNBX_ERR_ARG, "bad `want` mask"};
+        if ((want & PNBX_WANT_POT) && !out_pot && m > 0) throw ArgError{PNBX_ERR_ARG, "out_pot is NULL"};
+        if ((want & PNBX_WANT_ACC) && !out_acc && m > 0) throw ArgError{PNBX_ERR_ARG, "out_acc is NULL"};
+        const bool self = tgt_pos == nullptr;
+        if (self && (tgt_begin < 0 || tgt_begin + m > n)) throw ArgError{PNBX_ERR_ARG, "target shard outside [0, N)"};
+        if (n >= (int64_t)1 << 31 || m >= (int64_t)1 << 40) throw ArgError{PNBX_ERR_ARG, "problem too large"};
+
+        Exec ex = make_exec(opts);
+        StageTimer tm(ex.stream);
+        if (m == 0) { finish_exec(ex); return; }
+
+        OutArray<double> o_pot, o_acc;
+        if (want & PNBX_WANT_POT) o_pot.bind(out_pot, (size_t)m, ex);
+        if (want & PNBX_WANT_ACC) o_acc.bind(out_acc, (size_t)3 * m, ex);
+        if (n == 0) {  // direct.rs:195-197: zeros
+            if (o_pot.d) PNBX_CUDA(cudaMemsetAsync(o_pot.d, 0, (size_t)m * sizeof(double), ex.stream));
+            if (o_acc.d) PNBX_CUDA(cudaMemsetAsync(o_acc.d, 0, (size_t)3 * m * sizeof(double), ex.stream));
+        } else {
+            tm.begin("direct.h2d");
+            InArray<double> i_pos, i_mass, i_h, i_tgt;
+            i_pos.bind(src_pos, (size_t)3 * n, ex);
+            i_mass.bind(src_mass, (size_t)n, ex);
+            i_h.bind(src_h, (size_t)n, ex);
+            if (!self) i_tgt.bind(tgt_pos, (size_t)3 * m, ex);
+            tm.end();
+            if (ex.f64)
+                run_direct<double, TILE64>(ex, i_pos.d, i_mass.d, i_h.d, n, i_tgt.d, m, tgt_begin, kernel, want, o_pot.d,
+                                           o_acc.d, tm);
+            else
+                run_direct<float, TILE32>(ex, i_pos.d, i_mass.d, i_h.d, n, i_tgt.d, m, tgt_begin, kernel, want, o_pot.d,
+                                          o_acc.d, tm);
+        }
+        tm.begin("direct.d2h");
+        o_pot.finish(ex);
+        o_acc.finish(ex);
+        tm.end();
+        finish_exec(ex);
+    });
+}
