@@ -66,7 +66,8 @@ typedef struct pnbx_opts {
     int32_t mem_space; /* PNBX_MEM_HOST | PNBX_MEM_DEVICE                           */
     int32_t precision; /* PNBX_PREC_F32 (default) | PNBX_PREC_F64                   */
     int32_t flags;     /* bit mask of PNBX_FLAG_*                                 */
-    void* stream;      /* cudaStream_t to order work on; NULL = library stream    */
+    void* stream;      /* cudaStream_t to order work on. NULL = a library-owned stream for
+                          PNBX_MEM_HOST, the CUDA default stream for PNBX_MEM_DEVICE */
 } pnbx_opts;
 
 typedef struct pnbx_tree pnbx_tree; /* opaque; owns device copies of the sources */

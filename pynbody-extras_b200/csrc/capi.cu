@@ -75,7 +75,8 @@ Exec make_exec(const pnbx_opts* opts) {
     ex.kernel_events = opts && (opts->flags & PNBX_FLAG_KERNEL_EVENTS);
     kernel_events().armed = ex.kernel_events;
     if (ex.kernel_events) kernel_events().valid = false;
-    if (opts && opts->stream) {
+    if (opts && (opts->stream || ex.device_ptrs)) {
+        // device pointers are ordered against the caller's stream: NULL means the CUDA default stream
         ex.stream = (cudaStream_t)opts->stream;
     } else {
         // one library stream per (thread, device), created lazily and kept

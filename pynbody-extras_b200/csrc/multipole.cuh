@@ -1,0 +1,315 @@
+// multipole.cuh — Cartesian multipoles to order 5 on the device.
+//
+// Conventions follow the reference (crates/gravity/src/multipole.rs): coefficient
+// M_lmn = sum m x^l y^m z^n / (l! m! n!) about the node's centre of mass, stored in the
+// reference's field order (multipole.rs:11-74) so dumps compare 1:1 with the oracle.
+//   P2M  : multipole.rs:82-170      (float64, same operation order -> bit-equal payloads)
+//   M2M  : multipole.rs:1536-1595   (float64, same loop and accumulation order)
+//   D    : derivatives of 1/r, multipole.rs:591-856, 1216-1349 (templated: f32 walk / f64 check)
+//   M2P  : multipole.rs:858-1025, 1352-1528 (potential has no dipole term; acceleration at
+//          order p uses moments through order p-1 — SURVEY F9)
+#pragma once
+#include <cfloat>
+#include <cstdint>
+
+namespace pnbx {
+namespace mp {
+
+// index of coefficient (l,m,n) in reference field order
+enum : int {
+    I000, I100, I010, I001, I200, I020, I002, I110, I101, I011, I300, I030, I003, I210, I201, I120, I102, I021, I012,
+    I111, I400, I040, I004, I310, I301, I130, I103, I031, I013, I220, I202, I022, I211, I121, I112, I500, I050, I005,
+    I410, I401, I140, I104, I041, I014, I320, I302, I230, I203, I032, I023, I221, I212, I122, I311, I131, I113, NCOEF
+};
+
+// coefficients kept per node for a given multipole_order (MultipoleMoments::from_full, multipole.rs:270-279)
+__host__ __device__ constexpr int stored_coeffs(int order) {
+    return order <= 1 ? 1 : order == 2 ? 10 : order == 3 ? 20 : order == 4 ? 35 : 56;
+}
+
+struct Lmn {
+    int8_t l, m, n;
+};
+// exponent triples in field order
+__device__ constexpr Lmn kLmn[NCOEF] = {
+    {0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {1, 1, 0}, {1, 0, 1}, {0, 1, 1},
+    {3, 0, 0}, {0, 3, 0}, {0, 0, 3}, {2, 1, 0}, {2, 0, 1}, {1, 2, 0}, {1, 0, 2}, {0, 2, 1}, {0, 1, 2}, {1, 1, 1},
+    {4, 0, 0}, {0, 4, 0}, {0, 0, 4}, {3, 1, 0}, {3, 0, 1}, {1, 3, 0}, {1, 0, 3}, {0, 3, 1}, {0, 1, 3}, {2, 2, 0},
+    {2, 0, 2}, {0, 2, 2}, {2, 1, 1}, {1, 2, 1}, {1, 1, 2}, {5, 0, 0}, {0, 5, 0}, {0, 0, 5}, {4, 1, 0}, {4, 0, 1},
+    {1, 4, 0}, {1, 0, 4}, {0, 4, 1}, {0, 1, 4}, {3, 2, 0}, {3, 0, 2}, {2, 3, 0}, {2, 0, 3}, {0, 3, 2}, {0, 2, 3},
+    {2, 2, 1}, {2, 1, 2}, {1, 2, 2}, {3, 1, 1}, {1, 3, 1}, {1, 1, 3}};
+
+// (l,m,n) -> field index; only l+m+n <= 5 is ever looked up
+__device__ inline int lmn_index(int l, int m, int n) {
+    // small perfect hash over the 56 valid triples: search the order block (at most 21 entries)
+    const int o = l + m + n;
+    const int lo = o == 0 ? 0 : o == 1 ? 1 : o == 2 ? 4 : o == 3 ? 10 : o == 4 ? 20 : 35;
+    const int hi = o == 0 ? 1 : o == 1 ? 4 : o == 2 ? 10 : o == 3 ? 20 : o == 4 ? 35 : 56;
+    for (int i = lo; i < hi; ++i)
+        if (kLmn[i].l == l && kLmn[i].m == m) return i;  // n is implied by the order block
+    return -1;
+}
+
+// ---- P2M ---------------------------------------------------------------------------------------
+// Each coefficient adds  ((c * mass) * f1) * f2 ...  with the factor sequence the reference
+// writes (e.g. m120 += 0.5*mass*y*y*x). A factor is a coordinate (power 1) or a powi() value.
+// Encoded as up to 5 tokens, token = axis*8 + power, 0 = end.
+struct P2MTerm {
+    double c;
+    uint8_t tok[5];
+};
+#define PX(p) (uint8_t)(0 * 8 + (p))
+#define PY(p) (uint8_t)(1 * 8 + (p))
+#define PZ(p) (uint8_t)(2 * 8 + (p))
+__device__ constexpr P2MTerm kP2M[NCOEF] = {
+    {1.0, {0, 0, 0, 0, 0}},  // m000 += mass
+    {1.0, {PX(1)}}, {1.0, {PY(1)}}, {1.0, {PZ(1)}},
+    {0.5, {PX(1), PX(1)}}, {0.5, {PY(1), PY(1)}}, {0.5, {PZ(1), PZ(1)}},
+    {1.0, {PX(1), PY(1)}}, {1.0, {PX(1), PZ(1)}}, {1.0, {PY(1), PZ(1)}},
+    {1.0 / 6.0, {PX(3)}}, {1.0 / 6.0, {PY(3)}}, {1.0 / 6.0, {PZ(3)}},
+    {0.5, {PX(1), PX(1), PY(1)}}, {0.5, {PX(1), PX(1), PZ(1)}}, {0.5, {PY(1), PY(1), PX(1)}},
+    {0.5, {PX(1), PZ(1), PZ(1)}}, {0.5, {PY(1), PY(1), PZ(1)}}, {0.5, {PY(1), PZ(1), PZ(1)}},
+    {1.0, {PX(1), PY(1), PZ(1)}},
+    {1.0 / 24.0, {PX(4)}}, {1.0 / 24.0, {PY(4)}}, {1.0 / 24.0, {PZ(4)}},
+    {1.0 / 6.0, {PX(3), PY(1)}}, {1.0 / 6.0, {PX(3), PZ(1)}}, {1.0 / 6.0, {PY(3), PX(1)}},
+    {1.0 / 6.0, {PX(1), PZ(3)}}, {1.0 / 6.0, {PY(3), PZ(1)}}, {1.0 / 6.0, {PY(1), PZ(3)}},
+    {0.25, {PX(1), PX(1), PY(1), PY(1)}}, {0.25, {PX(1), PX(1), PZ(1), PZ(1)}}, {0.25, {PY(1), PY(1), PZ(1), PZ(1)}},
+    {0.5, {PX(1), PX(1), PY(1), PZ(1)}}, {0.5, {PY(1), PY(1), PX(1), PZ(1)}}, {0.5, {PZ(1), PZ(1), PX(1), PY(1)}},
+    {1.0 / 120.0, {PX(5)}}, {1.0 / 120.0, {PY(5)}}, {1.0 / 120.0, {PZ(5)}},
+    {1.0 / 24.0, {PX(4), PY(1)}}, {1.0 / 24.0, {PX(4), PZ(1)}}, {1.0 / 24.0, {PY(4), PX(1)}},
+    {1.0 / 24.0, {PZ(4), PX(1)}}, {1.0 / 24.0, {PY(4), PZ(1)}}, {1.0 / 24.0, {PZ(4), PY(1)}},
+    {1.0 / 12.0, {PX(3), PY(2)}}, {1.0 / 12.0, {PX(3), PZ(2)}}, {1.0 / 12.0, {PX(2), PY(3)}},
+    {1.0 / 12.0, {PX(2), PZ(3)}}, {1.0 / 12.0, {PY(3), PZ(2)}}, {1.0 / 12.0, {PY(2), PZ(3)}},
+    {0.25, {PX(1), PX(1), PY(1), PY(1), PZ(1)}}, {0.25, {PX(1), PX(1), PZ(1), PZ(1), PY(1)}},
+    {0.25, {PY(1), PY(1), PZ(1), PZ(1), PX(1)}},
+    {1.0 / 6.0, {PX(3), PY(1), PZ(1)}}, {1.0 / 6.0, {PY(3), PX(1), PZ(1)}}, {1.0 / 6.0, {PZ(3), PX(1), PY(1)}}};
+#undef PX
+#undef PY
+#undef PZ
+
+// integer power by square-and-multiply, the operation order of compiler-rt's __powidf2 (f64::powi)
+__device__ inline double powi_rn(double a, int b) {
+    double r = 1.0;
+    for (;;) {
+        if (b & 1) r = __dmul_rn(r, a);
+        b >>= 1;
+        if (b == 0) break;
+        a = __dmul_rn(a, a);
+    }
+    return r;
+}
+
+// accumulate one particle (offset x,y,z from the expansion centre) into mom[0..ncoef)
+__device__ inline void p2m_accumulate(double* mom, int ncoef, double mass, double x, double y, double z) {
+    double pw[3][6];
+    const double v[3] = {x, y, z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        pw[a][1] = v[a];
+#pragma unroll
+        for (int p = 2; p <= 5; ++p) pw[a][p] = powi_rn(v[a], p);
+    }
+    mom[0] = __dadd_rn(mom[0], mass);
+    for (int i = 1; i < ncoef; ++i) {
+        double t = __dmul_rn(kP2M[i].c, mass);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int tok = kP2M[i].tok[k];
+            if (tok == 0) break;
+            t = __dmul_rn(t, pw[tok >> 3][tok & 7]);
+        }
+        mom[i] = __dadd_rn(mom[i], t);
+    }
+}
+
+// ---- M2M ---------------------------------------------------------------------------------------
+// out[lmn] = sum_{i<=l, j<=m, k<=n} (-1)^(d) shift^d / d! * child[ijk],  d = (l-i, m-j, n-k),
+// accumulated in the reference's loop order; `acc` += out (add_assign, multipole.rs:173-230).
+__device__ inline void m2m_accumulate(double* acc, const double* child, int order, int ncoef, const double shift[3]) {
+    const double fact[6] = {1.0, 1.0, 2.0, 6.0, 24.0, 120.0};
+    double spw[3][6];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        spw[a][0] = 1.0;
+#pragma unroll
+        for (int p = 1; p <= 5; ++p) spw[a][p] = powi_rn(shift[a], p);
+    }
+    for (int t = 0; t < ncoef; ++t) {
+        const int l = kLmn[t].l, m = kLmn[t].m, n = kLmn[t].n;
+        if (l + m + n > order) continue;
+        double sum = 0.0;
+        for (int i = 0; i <= l; ++i)
+            for (int j = 0; j <= m; ++j)
+                for (int k = 0; k <= n; ++k) {
+                    const double base = child[lmn_index(i, j, k)];
+                    if (base == 0.0) continue;
+                    const int dl = l - i, dm = m - j, dn = n - k;
+                    double pw = (dl + dm + dn == 0) ? 1.0 : __dmul_rn(__dmul_rn(spw[0][dl], spw[1][dm]), spw[2][dn]);
+                    const double sign = ((dl + dm + dn) & 1) ? -1.0 : 1.0;
+                    const double coeff = __ddiv_rn(__dmul_rn(sign, pw), __dmul_rn(__dmul_rn(fact[dl], fact[dm]), fact[dn]));
+                    sum = __dadd_rn(sum, __dmul_rn(coeff, base));
+                }
+        acc[t] = __dadd_rn(acc[t], sum);
+    }
+}
+
+// ---- derivatives of 1/r and M2P ----------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ T inv_sqrt(T x);
+template <>
+__device__ __forceinline__ float inv_sqrt<float>(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <>
+__device__ __forceinline__ double inv_sqrt<double>(double x) { return 1.0 / sqrt(x); }
+
+// D[lmn] = d^(l+m+n)/dx^l dy^m dz^n (1/r) up to total order DORD, r = |(dx,dy,dz)|, tiny added to r^2.
+// Built from the radial factors dt_k = (-1)^(k-1) (2k-3)!! / r^k times powers of the unit vector.
+template <int DORD, class T>
+__device__ __forceinline__ void derivatives(T dx, T dy, T dz, T tiny, T* D) {
+    const T r2 = dx * dx + dy * dy + dz * dz + tiny;
+    const T ri = inv_sqrt<T>(r2);
+    const T x = dx * ri, y = dy * ri, z = dz * ri;
+    const T t1 = ri;
+    D[I000] = t1;
+    if (DORD < 1) return;
+    T t2 = -t1 * ri;
+    D[I100] = t2 * x;
+    D[I010] = t2 * y;
+    D[I001] = t2 * z;
+    if (DORD < 2) return;
+    T t3 = T(-3) * t2 * ri;
+    const T x2 = x * x, y2 = y * y, z2 = z * z;
+    t2 *= ri;
+    D[I200] = t3 * x2 + t2;
+    D[I020] = t3 * y2 + t2;
+    D[I002] = t3 * z2 + t2;
+    D[I110] = t3 * x * y;
+    D[I101] = t3 * x * z;
+    D[I011] = t3 * y * z;
+    if (DORD < 3) return;
+    T t4 = T(-5) * t3 * ri;
+    const T x3 = x2 * x, y3 = y2 * y, z3 = z2 * z;
+    t3 *= ri;
+    D[I300] = t4 * x3 + T(3) * t3 * x;
+    D[I030] = t4 * y3 + T(3) * t3 * y;
+    D[I003] = t4 * z3 + T(3) * t3 * z;
+    D[I210] = t4 * x2 * y + t3 * y;
+    D[I201] = t4 * x2 * z + t3 * z;
+    D[I120] = t4 * y2 * x + t3 * x;
+    D[I102] = t4 * z2 * x + t3 * x;
+    D[I021] = t4 * y2 * z + t3 * z;
+    D[I012] = t4 * z2 * y + t3 * y;
+    D[I111] = t4 * x * y * z;
+    if (DORD < 4) return;
+    T t5 = T(-7) * t4 * ri;
+    const T x4 = x3 * x, y4 = y3 * y, z4 = z3 * z;
+    t3 *= ri;
+    t4 *= ri;
+    D[I400] = t5 * x4 + T(6) * t4 * x2 + T(3) * t3;
+    D[I040] = t5 * y4 + T(6) * t4 * y2 + T(3) * t3;
+    D[I004] = t5 * z4 + T(6) * t4 * z2 + T(3) * t3;
+    D[I310] = t5 * x3 * y + T(3) * t4 * x * y;
+    D[I301] = t5 * x3 * z + T(3) * t4 * x * z;
+    D[I130] = t5 * y3 * x + T(3) * t4 * y * x;
+    D[I103] = t5 * z3 * x + T(3) * t4 * x * z;
+    D[I031] = t5 * y3 * z + T(3) * t4 * z * y;
+    D[I013] = t5 * z3 * y + T(3) * t4 * z * y;
+    D[I220] = t5 * x2 * y2 + t4 * (x2 + y2) + t3;
+    D[I202] = t5 * x2 * z2 + t4 * (x2 + z2) + t3;
+    D[I022] = t5 * y2 * z2 + t4 * (y2 + z2) + t3;
+    D[I211] = t5 * x2 * y * z + t4 * y * z;
+    D[I121] = t5 * y2 * x * z + t4 * x * z;
+    D[I112] = t5 * z2 * x * y + t4 * x * y;
+    if (DORD < 5) return;
+    const T t6 = T(-9) * t5 * ri;
+    const T x5 = x4 * x, y5 = y4 * y, z5 = z4 * z;
+    t4 *= ri;
+    t5 *= ri;
+    D[I500] = t6 * x5 + T(10) * t5 * x3 + T(15) * t4 * x;
+    D[I050] = t6 * y5 + T(10) * t5 * y3 + T(15) * t4 * y;
+    D[I005] = t6 * z5 + T(10) * t5 * z3 + T(15) * t4 * z;
+    D[I410] = t6 * x4 * y + T(6) * t5 * x2 * y + T(3) * t4 * y;
+    D[I401] = t6 * x4 * z + T(6) * t5 * x2 * z + T(3) * t4 * z;
+    D[I140] = t6 * y4 * x + T(6) * t5 * y2 * x + T(3) * t4 * x;
+    D[I041] = t6 * y4 * z + T(6) * t5 * y2 * z + T(3) * t4 * z;
+    D[I104] = t6 * z4 * x + T(6) * t5 * z2 * x + T(3) * t4 * x;
+    D[I014] = t6 * z4 * y + T(6) * t5 * z2 * y + T(3) * t4 * y;
+    D[I320] = t6 * x3 * y2 + t5 * x3 + T(3) * t5 * x * y2 + T(3) * t4 * x;
+    D[I302] = t6 * x3 * z2 + t5 * x3 + T(3) * t5 * x * z2 + T(3) * t4 * x;
+    D[I230] = t6 * y3 * x2 + t5 * y3 + T(3) * t5 * y * x2 + T(3) * t4 * y;
+    D[I032] = t6 * y3 * z2 + t5 * y3 + T(3) * t5 * y * z2 + T(3) * t4 * y;
+    D[I203] = t6 * z3 * x2 + t5 * z3 + T(3) * t5 * z * x2 + T(3) * t4 * z;
+    D[I023] = t6 * z3 * y2 + t5 * z3 + T(3) * t5 * z * y2 + T(3) * t4 * z;
+    D[I311] = t6 * x3 * y * z + T(3) * t5 * x * y * z;
+    D[I131] = t6 * y3 * x * z + T(3) * t5 * x * y * z;
+    D[I113] = t6 * z3 * x * y + T(3) * t5 * x * y * z;
+    D[I122] = t6 * x * y2 * z2 + t5 * x * y2 + t5 * x * z2 + t4 * x;
+    D[I212] = t6 * y * x2 * z2 + t5 * y * x2 + t5 * y * z2 + t4 * y;
+    D[I221] = t6 * z * x2 * y2 + t5 * z * x2 + t5 * z * y2 + t4 * z;
+}
+
+// phi = - sum_{order != 1} M_lmn D_lmn  through `ORDER` (no dipole term, multipole.rs:866-917)
+template <int ORDER, class T>
+__device__ __forceinline__ T m2p_potential(const T* M, const T* D) {
+    T phi = -M[I000] * D[I000];
+    if (ORDER >= 2) {
+#pragma unroll
+        for (int i = I200; i <= I011; ++i) phi -= M[i] * D[i];
+    }
+    if (ORDER >= 3) {
+#pragma unroll
+        for (int i = I300; i <= I111; ++i) phi -= M[i] * D[i];
+    }
+    if (ORDER >= 4) {
+#pragma unroll
+        for (int i = I400; i <= I112; ++i) phi -= M[i] * D[i];
+    }
+    if (ORDER >= 5) {
+#pragma unroll
+        for (int i = I500; i <= I113; ++i) phi -= M[i] * D[i];
+    }
+    return phi;
+}
+
+// a_x = - sum M_lmn D_(l+1)mn etc. with moments through order ORDER-1 (multipole.rs:927-1025, 1408-1528)
+template <int ORDER, class T>
+__device__ __forceinline__ void m2p_accel(const T* M, const T* D, T& ax, T& ay, T& az) {
+    ax = -M[I000] * D[I100];
+    ay = -M[I000] * D[I010];
+    az = -M[I000] * D[I001];
+    if (ORDER >= 2) {
+        ax -= M[I100] * D[I200] + M[I010] * D[I110] + M[I001] * D[I101];
+        ay -= M[I100] * D[I110] + M[I010] * D[I020] + M[I001] * D[I011];
+        az -= M[I100] * D[I101] + M[I010] * D[I011] + M[I001] * D[I002];
+    }
+    if (ORDER >= 3) {
+        ax -= M[I200] * D[I300] + M[I020] * D[I120] + M[I002] * D[I102] + M[I110] * D[I210] + M[I101] * D[I201] + M[I011] * D[I111];
+        ay -= M[I200] * D[I210] + M[I020] * D[I030] + M[I002] * D[I012] + M[I110] * D[I120] + M[I101] * D[I111] + M[I011] * D[I021];
+        az -= M[I200] * D[I201] + M[I020] * D[I021] + M[I002] * D[I003] + M[I110] * D[I111] + M[I101] * D[I102] + M[I011] * D[I012];
+    }
+    if (ORDER >= 4) {
+        ax -= M[I003] * D[I103] + M[I012] * D[I112] + M[I021] * D[I121] + M[I030] * D[I130] + M[I102] * D[I202] +
+              M[I111] * D[I211] + M[I120] * D[I220] + M[I201] * D[I301] + M[I210] * D[I310] + M[I300] * D[I400];
+        ay -= M[I003] * D[I013] + M[I012] * D[I022] + M[I021] * D[I031] + M[I030] * D[I040] + M[I102] * D[I112] +
+              M[I111] * D[I121] + M[I120] * D[I130] + M[I201] * D[I211] + M[I210] * D[I220] + M[I300] * D[I310];
+        az -= M[I003] * D[I004] + M[I012] * D[I013] + M[I021] * D[I022] + M[I030] * D[I031] + M[I102] * D[I103] +
+              M[I111] * D[I112] + M[I120] * D[I121] + M[I201] * D[I202] + M[I210] * D[I211] + M[I300] * D[I301];
+    }
+    if (ORDER >= 5) {
+        ax -= M[I004] * D[I104] + M[I013] * D[I113] + M[I022] * D[I122] + M[I031] * D[I131] + M[I040] * D[I140] +
+              M[I103] * D[I203] + M[I112] * D[I212] + M[I121] * D[I221] + M[I130] * D[I230] + M[I202] * D[I302] +
+              M[I211] * D[I311] + M[I220] * D[I320] + M[I301] * D[I401] + M[I310] * D[I410] + M[I400] * D[I500];
+        ay -= M[I004] * D[I014] + M[I013] * D[I023] + M[I022] * D[I032] + M[I031] * D[I041] + M[I040] * D[I050] +
+              M[I103] * D[I113] + M[I112] * D[I122] + M[I121] * D[I131] + M[I130] * D[I140] + M[I202] * D[I212] +
+              M[I211] * D[I221] + M[I220] * D[I230] + M[I301] * D[I311] + M[I310] * D[I320] + M[I400] * D[I410];
+        az -= M[I004] * D[I005] + M[I013] * D[I014] + M[I022] * D[I023] + M[I031] * D[I032] + M[I040] * D[I041] +
+              M[I103] * D[I104] + M[I112] * D[I113] + M[I121] * D[I122] + M[I130] * D[I131] + M[I202] * D[I203] +
+              M[I211] * D[I212] + M[I220] * D[I221] + M[I301] * D[I302] + M[I310] * D[I311] + M[I400] * D[I401];
+    }
+}
+
+}  // namespace mp
+}  // namespace pnbx

@@ -1,0 +1,80 @@
+// tree.cuh — device-resident octree shared by tree_build.cu and tree_walk.cu.
+//
+// Topology reproduces the reference's recursive bucket octree (tree.rs:804-864) exactly, including
+// its node numbering (creation order), but is built without recursion: float64 octant-path keys by
+// the reference's own descent arithmetic, radix sort, level-by-level node emission from sorted key
+// ranges, then a renumbering pass.
+#pragma once
+#include "common.cuh"
+
+namespace pnbx {
+
+constexpr int KEY_LEVELS_HI = 21;  // 3 bits per level in a 64-bit word (63 bits used)
+constexpr int KEY_LEVELS = 42;     // hi + lo words
+
+// 32-byte record fetched on every node visit (one broadcast load per warp).
+struct alignas(32) NodeGeom {
+    double com[3];
+    double size2;  // (2*half)^2, tree.rs:794-798
+};
+// 16-byte control record.
+struct alignas(16) NodeCtl {
+    int32_t next_branch;  // tree.rs:736-776; -1 = end of walk
+    int32_t first;        // internal: first_subnode; leaf: first particle (sorted order)
+    int32_t kind;         // >= 0: leaf with `kind` particles; -1: internal; -2: zero mass (skip subtree)
+    int32_t pad;
+};
+
+struct pnbx_tree_impl {
+    int device = 0;
+    int64_t n = 0;
+    int64_t leaf_capacity = 1;
+    int order = 0;   // multipole_order clamped to 5
+    int order_raw = 0;
+    int kernel = PNBX_KERNEL_PLUMMER;
+    bool has_mass = false, has_h = false, has_payload = false, has_hmax = false;
+
+    // sources, original order (owned copies, gravity.rs:154-180)
+    DevBuf<double> pos, mass, h;
+    // root cube (tree.rs:628-654), host copies
+    double root_center[3] = {0, 0, 0};
+    double root_half = 0;
+
+    // per particle
+    DevBuf<uint64_t> key_hi, key_lo;   // original order
+    DevBuf<uint32_t> perm;             // sorted position -> original index (ascending inside a leaf)
+    DevBuf<uint32_t> inv_perm;         // original index -> sorted position
+    // sorted copies used by payload builds and the walk
+    DevBuf<double> spos;               // (n,3) float64
+    DevBuf<double> smass, sh;          // float64 (smass only if has_mass, sh only if has_h)
+    DevBuf<float4> src32;              // (x-cx, y-cy, z-cz, m) float32 relative to the root centre
+    DevBuf<float> sh32;
+
+    // nodes, reference numbering
+    int64_t nn = 0, n_leaves = 0;
+    int depth = 0;
+    DevBuf<double> center, half;       // (nn,3), (nn)
+    DevBuf<uint8_t> node_depth, node_nchild;
+    DevBuf<uint32_t> node_start, node_count;  // particle range in sorted order (all nodes)
+    DevBuf<int32_t> first_subnode, next_branch;
+    DevBuf<uint64_t> path_hi, path_lo;
+    // level structure in reference ids (for bottom-up payload sweeps): ids of level d are
+    // level_ids[level_off[d] .. level_off[d+1])
+    DevBuf<int32_t> level_ids;
+    std::vector<int64_t> level_off;
+    DevBuf<int32_t> parent;            // reference id of the parent (-1 for the root)
+
+    // payloads
+    DevBuf<double> nmass, ncom, hmax;  // (nn), (nn,3), (nn)
+    int n_moments = 0;
+    DevBuf<double> moments;            // (nn, n_moments) float64
+    DevBuf<float> moments32;           // same, float32 for the walk
+    DevBuf<NodeGeom> geom;
+    DevBuf<NodeCtl> ctl;
+};
+
+// tree_walk.cu
+void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int64_t m, int64_t tgt_begin,
+               double theta, int want, double* d_pot, double* d_acc, StageTimer& tm);
+
+}  // namespace pnbx

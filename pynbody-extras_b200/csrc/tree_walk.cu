@@ -1,0 +1,378 @@
+// tree_walk.cu — K7: warp-cooperative, lane-exact tree walk (tree.rs:1069-1370, leaf sums :97-417).
+//
+// One warp walks 32 key-adjacent targets through the *union* of their reference paths with the
+// reference's stackless links (first_subnode / next_branch). Every node record is fetched once per
+// warp (all lanes read the same address: one broadcast transaction), each lane evaluates its OWN
+// opening criterion in float64 on the float64 COM — `size2 < theta^2 * dist2` plus the hmax
+// softening gate (tree.rs:55-71, 1117-1126) — so each target's interaction list is exactly the
+// reference's (leaves are always summed particle by particle). A lane that accepts a node
+// which other lanes must open is parked until the warp reaches that node's next_branch.
+// Interactions (leaf pairs, multipole M2P) run in fp32 (or fp64 in verification mode) and are folded
+// into float64 accumulators once per node.
+#include <cub/cub.cuh>
+
+#include "multipole.cuh"
+#include "tree.cuh"
+
+namespace pnbx {
+namespace {
+
+constexpr int WT = 128;  // threads per block (4 independent warps)
+
+template <class T>
+struct Vec4T {
+    T x, y, z, w;
+};
+
+template <class T>
+struct WalkArgs {
+    const NodeGeom* geom;
+    const NodeCtl* ctl;
+    const double* hmax;   // nullable
+    const T* moments;     // (nn, K)
+    int K;
+    const void* src;      // float4 (T=float) or double spos/smass (T=double)
+    const double* spos;   // sorted float64 positions
+    const double* smass;  // sorted float64 masses (nullable -> 1)
+    const T* src_h;       // sorted softenings in T (nullable)
+    const double* sh;     // sorted softenings float64 (nullable)
+    const uint32_t* perm; // sorted position -> original index
+    // targets
+    int64_t m;
+    int self;                 // 1: targets are tree particles
+    const uint32_t* tlist;    // self: sorted positions to evaluate (nullable = identity)
+    int64_t tgt_begin;        // self: output slot = perm[s] - tgt_begin
+    const double* tgt;        // points: (m,3) float64
+    const uint32_t* torder;   // points: walk order -> point index
+    double theta2;
+    double rc[3];             // root centre (origin of the fp32 coordinates)
+    int kernel;               // PNBX_KERNEL_PLUMMER | PNBX_KERNEL_SPLINE
+    double* out_pot;
+    double* out_acc;
+};
+
+template <class T>
+__device__ __forceinline__ T tiny_v();
+template <>
+__device__ __forceinline__ float tiny_v<float>() { return FLT_MIN; }
+template <>
+__device__ __forceinline__ double tiny_v<double>() { return DBL_MIN; }
+
+template <class T>
+__device__ __forceinline__ T w2_in(T u) {  // kernel.rs:84-102, u < 1
+    T u2 = u * u;
+    if (u < T(0.5)) return T(16.0 / 3.0) * u2 + u2 * u2 * (T(32.0 / 5.0) * u - T(48.0 / 5.0)) - T(14.0 / 5.0);
+    return T(1.0 / 15.0) / u + u2 * (T(32.0 / 3.0) + u * (T(-16.0) + u * (T(48.0 / 5.0) - T(32.0 / 15.0) * u))) - T(16.0 / 5.0);
+}
+template <class T>
+__device__ __forceinline__ T w2p_in(T u) {  // kernel.rs:108-124, u < 1
+    T u2 = u * u;
+    if (u < T(0.5)) return u * (T(32.0 / 3.0) + u2 * (T(32.0) * u - T(192.0 / 5.0)));
+    return T(-1.0 / 15.0) / u2 + u * (T(64.0 / 3.0) + u * (T(-48.0) + u * (T(192.0 / 5.0) - T(32.0 / 3.0) * u)));
+}
+
+// source particle p in T, relative to the root centre
+template <class T>
+__device__ __forceinline__ Vec4T<T> load_src(const WalkArgs<T>& a, int p);
+template <>
+__device__ __forceinline__ Vec4T<float> load_src<float>(const WalkArgs<float>& a, int p) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(a.src) + p);
+    return {v.x, v.y, v.z, v.w};
+}
+template <>
+__device__ __forceinline__ Vec4T<double> load_src<double>(const WalkArgs<double>& a, int p) {
+    return {a.spos[3 * (int64_t)p] - a.rc[0], a.spos[3 * (int64_t)p + 1] - a.rc[1], a.spos[3 * (int64_t)p + 2] - a.rc[2],
+            a.smass ? a.smass[p] : 1.0};
+}
+
+template <int ORDER, int WANT, class T>
+__global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
+    constexpr int DORD = (WANT & PNBX_WANT_ACC) ? (ORDER < 1 ? 1 : ORDER) : (ORDER < 2 ? 0 : ORDER);
+    constexpr unsigned FULL = 0xffffffffu;
+    const int64_t k = (int64_t)blockIdx.x * WT + threadIdx.x;
+    const bool valid = k < a.m;
+    // ---- this lane's target
+    double tx = 0, ty = 0, tz = 0, th64 = 0;
+    int skip = -1;
+    int64_t oslot = 0;
+    bool has_th = false;
+    if (valid) {
+        if (a.self) {
+            const uint32_t s = a.tlist ? a.tlist[k] : (uint32_t)k;
+            tx = a.spos[3 * (int64_t)s]; ty = a.spos[3 * (int64_t)s + 1]; tz = a.spos[3 * (int64_t)s + 2];
+            skip = (int)s;
+            oslot = (int64_t)a.perm[s] - a.tgt_begin;
+            if (a.sh) { th64 = a.sh[s]; has_th = true; }  // target_h_opt = softenings[i] (tree.rs:1439)
+        } else {
+            const uint32_t q = a.torder[k];
+            tx = a.tgt[3 * (int64_t)q]; ty = a.tgt[3 * (int64_t)q + 1]; tz = a.tgt[3 * (int64_t)q + 2];
+            oslot = q;
+        }
+    }
+    const T fx = (T)(tx - a.rc[0]), fy = (T)(ty - a.rc[1]), fz = (T)(tz - a.rc[2]);
+    const T th = (T)fmax(th64, 0.0);              // clamped target softening (tree.rs:115)
+    const bool soft = a.src_h != nullptr;         // softenings_opt.is_some() (tree.rs:116)
+    const bool spline = a.kernel == PNBX_KERNEL_SPLINE;
+    const double csep = spline ? 1.0 : 2.8;       // kernel.rs:20-28
+    double P = 0.0, Ax = 0.0, Ay = 0.0, Az = 0.0;
+
+    bool active = valid;
+    int resume = INT_MIN;
+    int idx = __ballot_sync(FULL, valid) ? 0 : -1;
+    while (idx >= 0) {
+        const NodeCtl c = a.ctl[idx];
+        if (!active && resume == idx) active = true;
+        if (c.kind == -2) {  // zero mass: skip the subtree (tree.rs:1087-1090)
+            idx = c.next_branch;
+            continue;
+        }
+        if (c.kind >= 0) {  // leaf: always summed directly (tree.rs:1094-1112)
+            if (active) {
+                T pot = T(0), ax = T(0), ay = T(0), az = T(0);
+                for (int p = c.first; p < c.first + c.kind; ++p) {
+                    if (p == skip) continue;  // skip_self by index (tree.rs:130)
+                    const Vec4T<T> s = load_src<T>(a, p);
+                    const T dx = s.x - fx, dy = s.y - fy, dz = s.z - fz;
+                    T r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                    T h = T(0);
+                    if (soft) h = max(max(a.src_h[p], T(0)), th);  // tree.rs:234-235
+                    T kpot, g;
+                    if (spline && h > T(0) && r2 < h * h) {  // tree.rs:237-243 / 367-378
+                        const T rinv = mp::inv_sqrt<T>(r2 + tiny_v<T>());
+                        const T hinv = T(1) / h;
+                        const T u = (r2 + tiny_v<T>()) * rinv * hinv;
+                        kpot = w2_in(u) * hinv;
+                        g = w2p_in(u) * (hinv * hinv) * rinv;
+                    } else {
+                        if (!spline) r2 = fma(h, h, r2);  // Plummer: -1/sqrt(r^2+h^2), h = 0 is Newtonian
+                        const T rinv = mp::inv_sqrt<T>(r2 + tiny_v<T>());
+                        kpot = -rinv;
+                        g = rinv * rinv * rinv;
+                    }
+                    if (WANT & PNBX_WANT_POT) pot = fma(s.w, kpot, pot);
+                    if (WANT & PNBX_WANT_ACC) {
+                        const T mg = s.w * g;
+                        ax = fma(dx, mg, ax);
+                        ay = fma(dy, mg, ay);
+                        az = fma(dz, mg, az);
+                    }
+                }
+                if (WANT & PNBX_WANT_POT) P += (double)pot;
+                if (WANT & PNBX_WANT_ACC) { Ax += (double)ax; Ay += (double)ay; Az += (double)az; }
+            }
+            idx = c.next_branch;
+            continue;
+        }
+        // ---- internal node: per-lane opening decision in float64 (tree.rs:1114-1126)
+        const NodeGeom gm = a.geom[idx];
+        bool accept = false;
+        double dx = 0, dy = 0, dz = 0;
+        if (active) {
+            dx = gm.com[0] - tx;
+            dy = gm.com[1] - ty;
+            dz = gm.com[2] - tz;
+            const double dist2 = fma(dx, dx, fma(dy, dy, __dmul_rn(dz, dz))) + DBL_MIN;
+            bool soft_ok = true;
+            if (a.hmax) {  // node_soft_ok (tree.rs:55-71)
+                double h = fmax(a.hmax[idx], 0.0);
+                if (has_th) h = fmax(h, fmax(th64, 0.0));
+                if (h > 0.0) {
+                    const double ch = __dmul_rn(csep, h);
+                    soft_ok = dist2 > __dmul_rn(ch, ch);
+                }
+            }
+            accept = soft_ok && gm.size2 < __dmul_rn(a.theta2, dist2);
+        }
+        const unsigned need_open = __ballot_sync(FULL, active && !accept);
+        if (active && accept) {
+            const T* M = a.moments + (int64_t)idx * a.K;
+            T D[mp::NCOEF];
+            mp::derivatives<DORD, T>((T)dx, (T)dy, (T)dz, tiny_v<T>(), D);
+            if (ORDER <= 1) {
+                const T m0 = M[0];
+                if (WANT & PNBX_WANT_POT) P += (double)(-m0 * D[mp::I000]);
+                if (WANT & PNBX_WANT_ACC) {
+                    Ax += (double)(-m0 * D[mp::I100]);
+                    Ay += (double)(-m0 * D[mp::I010]);
+                    Az += (double)(-m0 * D[mp::I001]);
+                }
+            } else {
+                T Mr[mp::stored_coeffs(ORDER)];
+#pragma unroll
+                for (int i = 0; i < mp::stored_coeffs(ORDER); ++i) Mr[i] = M[i];
+                if (WANT & PNBX_WANT_POT) P += (double)mp::m2p_potential<ORDER, T>(Mr, D);
+                if (WANT & PNBX_WANT_ACC) {
+                    T ax, ay, az;
+                    mp::m2p_accel<ORDER, T>(Mr, D, ax, ay, az);
+                    Ax += (double)ax; Ay += (double)ay; Az += (double)az;
+                }
+            }
+        }
+        if (need_open) {
+            if (active && accept) {  // done with this subtree; wait for the warp at its next_branch
+                active = false;
+                resume = c.next_branch;
+            }
+            idx = c.first;
+        } else {
+            idx = c.next_branch;
+        }
+    }
+    if (valid) {
+        if (WANT & PNBX_WANT_POT) a.out_pot[oslot] = P;
+        if (WANT & PNBX_WANT_ACC) {
+            a.out_acc[3 * oslot] = Ax; a.out_acc[3 * oslot + 1] = Ay; a.out_acc[3 * oslot + 2] = Az;
+        }
+    }
+}
+
+template <class T>
+void launch_walk(int order, int want, const WalkArgs<T>& a, cudaStream_t s) {
+    const unsigned grid = (unsigned)ceil_div(a.m, WT);
+#define PNBX_W(O, W)                                                     \
+    if (order == O && want == W) {                                       \
+        PNBX_LAUNCH((walk_kernel<O, W, T>), grid, WT, 0, s, a);          \
+        return;                                                          \
+    }
+    PNBX_W(1, 1) PNBX_W(1, 2) PNBX_W(1, 3)
+    PNBX_W(2, 1) PNBX_W(2, 2) PNBX_W(2, 3)
+    PNBX_W(3, 1) PNBX_W(3, 2) PNBX_W(3, 3)
+    PNBX_W(4, 1) PNBX_W(4, 2) PNBX_W(4, 3)
+    PNBX_W(5, 1) PNBX_W(5, 2) PNBX_W(5, 3)
+#undef PNBX_W
+    throw ArgError{PNBX_ERR_ARG, "internal: no walk kernel variant"};
+}
+
+__global__ void point_keys(const double* __restrict__ pos, int64_t n, double cx, double cy, double cz, double hf0,
+                           uint64_t* __restrict__ key) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+    double hf = hf0;
+    uint64_t k = 0;
+    for (int l = 1; l <= KEY_LEVELS_HI; ++l) {
+        const unsigned ox = x >= cx, oy = y >= cy, oz = z >= cz;
+        k |= (uint64_t)(ox | (oy << 1) | (oz << 2)) << (3 * (KEY_LEVELS_HI - l));
+        const double off = hf * 0.5;
+        cx += ox ? off : -off;
+        cy += oy ? off : -off;
+        cz += oz ? off : -off;
+        hf = off;
+    }
+    key[i] = k;
+}
+__global__ void iota32(uint32_t* p, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+__global__ void shard_flags(const uint32_t* __restrict__ perm, int64_t n, int64_t lo, int64_t hi, uint8_t* __restrict__ f) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) f[s] = perm[s] >= lo && perm[s] < hi;
+}
+
+inline unsigned nb(int64_t n) { return (unsigned)std::max<int64_t>(1, ceil_div(n, 256)); }
+
+}  // namespace
+
+void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int64_t m, int64_t tgt_begin, double theta,
+               int want, double* d_pot, double* d_acc, StageTimer& tm) {
+    cudaStream_t s = ex.stream;
+    const bool self = d_tgt == nullptr;
+    DevBuf<uint32_t> tlist, torder;
+    tm.begin("octree.walk.prepare_targets");
+    if (self) {
+        if (!(tgt_begin == 0 && m == t.n)) {  // shard: sorted positions whose particle lies in [tgt_begin, tgt_begin+m)
+            DevBuf<uint8_t> flag((size_t)t.n, s);
+            DevBuf<int32_t> nsel(1, s);
+            tlist.alloc((size_t)t.n, s);
+            PNBX_LAUNCH(shard_flags, nb(t.n), 256, 0, s, t.perm.p, t.n, tgt_begin, tgt_begin + m, flag.p);
+            size_t bytes = 0;
+            cub::CountingInputIterator<uint32_t> it(0);
+            PNBX_CUDA(cub::DeviceSelect::Flagged(nullptr, bytes, it, flag.p, tlist.p, nsel.p, (int)t.n, s));
+            DevBuf<uint8_t> tmp(bytes, s);
+            PNBX_CUDA(cub::DeviceSelect::Flagged(tmp.get(), bytes, it, flag.p, tlist.p, nsel.p, (int)t.n, s));
+            ++launch_counter();
+        }
+    } else {
+        // walk the query points in path-key order so the 32 lanes of a warp share most of their path
+        DevBuf<uint64_t> key((size_t)m, s), key_s((size_t)m, s);
+        DevBuf<uint32_t> iota((size_t)m, s);
+        torder.alloc((size_t)m, s);
+        PNBX_LAUNCH(point_keys, nb(m), 256, 0, s, d_tgt, m, t.root_center[0], t.root_center[1], t.root_center[2],
+                    t.root_half, key.p);
+        PNBX_LAUNCH(iota32, nb(m), 256, 0, s, iota.p, m);
+        size_t bytes = 0;
+        PNBX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key.p, key_s.p, iota.p, torder.p, (int)m, 0, 63, s));
+        DevBuf<uint8_t> tmp(bytes, s);
+        PNBX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), bytes, key.p, key_s.p, iota.p, torder.p, (int)m, 0, 63, s));
+        ++launch_counter();
+    }
+    tm.end();
+
+    auto fill = [&](auto& a) {
+        a.geom = t.geom.p; a.ctl = t.ctl.p;
+        a.hmax = t.has_hmax ? t.hmax.p : nullptr;
+        a.K = t.n_moments;
+        a.spos = t.spos.p; a.smass = t.has_mass ? t.smass.p : nullptr;
+        a.sh = t.has_h ? t.sh.p : nullptr;
+        a.perm = t.perm.p;
+        a.m = m; a.self = self ? 1 : 0;
+        a.tlist = tlist.p; a.tgt_begin = tgt_begin; a.tgt = d_tgt; a.torder = torder.p;
+        a.theta2 = theta * theta;
+        a.rc[0] = t.root_center[0]; a.rc[1] = t.root_center[1]; a.rc[2] = t.root_center[2];
+        a.kernel = t.kernel;
+        a.out_pot = d_pot; a.out_acc = d_acc;
+    };
+    const int order = std::max(1, t.order);  // order 0 and 1 are both monopoles
+    tm.begin("octree.walk");
+    kernel_events().begin(s);
+    if (ex.f64) {
+        WalkArgs<double> a;
+        fill(a);
+        a.moments = t.moments.p; a.src = nullptr; a.src_h = t.has_h ? t.sh.p : nullptr;
+        launch_walk<double>(order, want, a, s);
+    } else {
+        WalkArgs<float> a;
+        fill(a);
+        a.moments = t.moments32.p; a.src = t.src32.p; a.src_h = t.has_h ? t.sh32.p : nullptr;
+        launch_walk<float>(order, want, a, s);
+    }
+    kernel_events().end(s);
+    PNBX_CUDA(cudaGetLastError());
+    tm.end();
+}
+
+}  // namespace pnbx
+
+using namespace pnbx;
+
+extern "C" int pnbx_tree_eval(pnbx_tree* tp, const double* tgt_pos, int64_t m, int64_t tgt_begin, double theta, int want,
+                              double* out_pot, double* out_acc, const pnbx_opts* opts) {
+    return guarded([&] {
+        if (!tp) throw ArgError{PNBX_ERR_ARG, "tree is NULL"};
+        auto& t = *reinterpret_cast<pnbx_tree_impl*>(tp);
+        if (!t.has_payload) throw ArgError{PNBX_ERR_STATE, "mass payload not built; call build_mass() before compute"};
+        if (!(want & (PNBX_WANT_POT | PNBX_WANT_ACC)) || (want & ~3)) throw ArgError{PNBX_ERR_ARG, "bad `want` mask"};
+        if (m < 0) throw ArgError{PNBX_ERR_ARG, "negative size"};
+        if ((want & PNBX_WANT_POT) && !out_pot && m > 0) throw ArgError{PNBX_ERR_ARG, "out_pot is NULL"};
+        if ((want & PNBX_WANT_ACC) && !out_acc && m > 0) throw ArgError{PNBX_ERR_ARG, "out_acc is NULL"};
+        const bool self = tgt_pos == nullptr;
+        if (self && (tgt_begin < 0 || tgt_begin + m > t.n)) throw ArgError{PNBX_ERR_ARG, "target shard outside [0, N)"};
+        if (m >= ((int64_t)1 << 31) - 16) throw ArgError{PNBX_ERR_ARG, "M must be < 2^31"};
+        pnbx_opts o = opts ? *opts : pnbx_opts{-1, PNBX_MEM_HOST, 0, 0, nullptr};
+        if (o.device < 0) o.device = t.device;
+        if (o.device != t.device) throw ArgError{PNBX_ERR_ARG, "tree lives on a different device"};
+        Exec ex = make_exec(&o);
+        StageTimer tm(ex.stream);
+        if (m == 0) { finish_exec(ex); return; }
+        OutArray<double> o_pot, o_acc;
+        if (want & PNBX_WANT_POT) o_pot.bind(out_pot, (size_t)m, ex);
+        if (want & PNBX_WANT_ACC) o_acc.bind(out_acc, (size_t)3 * m, ex);
+        InArray<double> i_tgt;
+        if (!self) i_tgt.bind(tgt_pos, (size_t)3 * m, ex);
+        tree_walk(t, ex, self ? nullptr : i_tgt.d, m, tgt_begin, theta, want, o_pot.d, o_acc.d, tm);
+        o_pot.finish(ex);
+        o_acc.finish(ex);
+        finish_exec(ex);
+    });
+}

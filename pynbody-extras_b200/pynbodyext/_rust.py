@@ -274,7 +274,9 @@ class Octree:
         _check(_load().pnbx_tree_set_kernel(self._h, _kernel_code(kernel, 0)))
 
     # -- compute (gravity.rs:267-444)
-    def _eval(self, points, theta, want, pname="points", tgt_begin=0, count=None, precision=None):
+    def _eval(self, points, theta, want, pname="points", tgt_begin=0, count=None, precision=None, method="compute"):
+        if not self.info()["has_payload"]:  # gravity.rs:274-278, 327-331, 356-360, 417-421
+            raise ValueError(f"mass payload not built; call build_mass() before {method}")
         tgt = None if points is None else _vec3(points, pname)
         m = (self._n if count is None else int(count)) if tgt is None else tgt.shape[0]
         pot = np.empty(m, dtype=np.float64) if want & WANT_POT else None
@@ -285,16 +287,16 @@ class Octree:
         return pot, acc
 
     def compute_accelerations(self, theta, threads=0):
-        return self._eval(None, theta, WANT_ACC)[1]
+        return self._eval(None, theta, WANT_ACC, method="compute_accelerations")[1]
 
     def compute_potentials(self, theta, threads=0):
-        return self._eval(None, theta, WANT_POT)[0]
+        return self._eval(None, theta, WANT_POT, method="compute_potentials")[0]
 
     def accelerations_at_points(self, points, theta, threads=0):
-        return self._eval(points, theta, WANT_ACC)[1]
+        return self._eval(points, theta, WANT_ACC, method="accelerations_at_points")[1]
 
     def potentials_at_points(self, points, theta, threads=0):
-        return self._eval(points, theta, WANT_POT)[0]
+        return self._eval(points, theta, WANT_POT, method="potentials_at_points")[0]
 
     # -- introspection used by the parity tests (not in the reference)
     def info(self) -> dict:

@@ -1,0 +1,266 @@
+"""GPU parity of the octree: topology + payloads bit-exact against the oracle's dump, tree results
+against the oracle's tree at the same (theta, leaf_capacity, order, kernel).
+
+Tolerances: node numbering, links, centres, half sizes, path keys, leaf particle lists, node mass,
+COM, hmax and multipole moments: EXACT (float64 bit equality). Tree potentials/accelerations:
+float64 verification mode <= 1e-11 RMS relative; fp32 interaction arithmetic <= 1e-5 RMS relative
+(BASELINE.json north_star), measured ~1e-7.
+"""
+import numpy as np
+import pytest
+
+from benchmarks.synthetic import hernquist, nfw_disc, plummer, uniform_cube
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-5
+TOL64 = 1e-11
+
+
+def rms_rel_vec(a, ref):
+    return np.sqrt((((a - ref) ** 2).sum(1) / (ref ** 2).sum(1)).mean())
+
+
+def rms_rel(p, ref):
+    return np.sqrt((((p - ref) / ref) ** 2).mean())
+
+
+def R():
+    import pynbodyext._rust as r
+    return r
+
+
+def leaf_sets(topo):
+    out = {}
+    for i in np.nonzero(topo["leaf_count"] >= 0)[0]:
+        s, c = topo["leaf_start"][i], topo["leaf_count"][i]
+        out[int(i)] = topo["leaf_particles"][s:s + c].tolist()
+    return out
+
+
+def assert_same_topology(g, o):
+    tg, to = g.topology(), o.topology()
+    ig, io = g.info(), o.info()
+    assert ig["n_nodes"] == io["n_nodes"] and ig["n_leaves"] == io["n_leaves"] and ig["depth"] == io["depth"]
+    for k in ("center", "half", "depth", "first_subnode", "next_branch", "leaf_count", "path_hi", "path_lo"):
+        assert np.array_equal(tg[k], to[k]), k
+    assert leaf_sets(tg) == leaf_sets(to)  # same particles, same (ascending) order in every leaf
+
+
+def assert_same_payload(g, o):
+    pg, po = g.payload(), o.payload()
+    assert np.array_equal(pg["mass"], po["mass"])
+    assert np.array_equal(pg["com"], po["com"])
+    if po["hmax"] is not None:
+        assert np.array_equal(pg["hmax"], po["hmax"])
+    assert pg["moments"].shape == po["moments"].shape
+    assert np.array_equal(pg["moments"], po["moments"])
+
+
+@pytest.mark.parametrize("n,cap,order", [(1, 8, 3), (7, 8, 0), (9, 8, 3), (300, 1, 2), (5000, 8, 3), (5000, 32, 5),
+                                         (20000, 8, 4), (3000, 128, 1)])
+def test_topology_and_payload_bit_exact(n, cap, order):
+    pos, m = plummer(n, seed=100 + n)
+    g = R().Octree(pos, m, cap, order)
+    o = O.Tree(pos, m, cap, order)
+    assert_same_topology(g, o)
+    assert_same_payload(g, o)
+
+
+def test_topology_clustered_deep_tree_uses_second_key_word():
+    # two tight clumps far apart: depth > 21 forces the 42-level key path
+    rng = np.random.default_rng(3)
+    a = rng.normal(0.0, 1e-9, (40, 3))
+    b = rng.normal(0.0, 1e-9, (40, 3)) + 1.0
+    pos = np.concatenate([a, b, rng.random((200, 3)) * 4 - 2])
+    m = rng.random(len(pos)) + 0.5
+    g = R().Octree(pos, m, 4, 3)
+    o = O.Tree(pos, m, 4, 3)
+    assert o.info()["depth"] > 21
+    assert_same_topology(g, o)
+    assert_same_payload(g, o)
+    p_g = g.compute_potentials(0.6)
+    p_o, _ = o.eval(0.6, want=1)
+    assert rms_rel(p_g, p_o) < TOL32
+
+
+def test_coincident_points_exceeding_leaf_capacity_raise():
+    pos = np.zeros((20, 3))
+    pos[10:] = 1.0
+    with pytest.raises(ValueError, match="deeper than 42 levels"):
+        R().Octree(pos, np.ones(20), 4, 0)
+
+
+def test_unit_mass_and_softening_payloads():
+    pos, _ = uniform_cube(4000, 5, with_masses=False)
+    h = np.random.default_rng(6).uniform(0.0, 0.1, 4000)
+    g = R().Octree(pos, None, 8, 3, h, 1)
+    o = O.Tree(pos, None, 8, 3, h, 1)
+    assert_same_topology(g, o)
+    with pytest.raises(ValueError, match="mass payload not built; call build_mass\\(\\) before compute_potentials"):
+        g.compute_potentials(0.5)
+    g.build_mass()
+    o.build_mass()
+    assert_same_payload(g, o)
+    p_g, p_o = g.compute_potentials(0.5), o.eval(0.5, want=1)[0]
+    assert rms_rel(p_g, p_o) < TOL32
+
+
+ORDERS = [0, 1, 2, 3, 4, 5]
+
+
+@pytest.mark.parametrize("order", ORDERS)
+def test_self_eval_matches_oracle_tree(order):
+    pos, m = hernquist(6000, seed=21)
+    g = R().Octree(pos, m, 8, order)
+    o = O.Tree(pos, m, 8, order)
+    for theta in (0.5, 0.7):
+        p_o, a_o = o.eval(theta)
+        p64, a64 = g._eval(None, theta, 3, precision="f64")
+        assert rms_rel(p64, p_o) < TOL64 and rms_rel_vec(a64, a_o) < TOL64
+        p32, a32 = g._eval(None, theta, 3)
+        assert rms_rel(p32, p_o) < TOL32 and rms_rel_vec(a32, a_o) < TOL32
+        assert np.array_equal(g.compute_potentials(theta), p32) and np.array_equal(g.compute_accelerations(theta), a32)
+
+
+@pytest.mark.parametrize("order", [0, 3, 5])
+def test_at_points_matches_oracle_tree(order):
+    pos, m = plummer(5000, seed=22)
+    q, _ = plummer(1500, seed=23, a=2.0)
+    q[:5] = pos[:5]  # points on top of particles: no skip in at-points mode (tree.rs:1516)
+    q[5] = [1e3, -2e3, 5e2]  # far outside the root cube
+    g = R().Octree(pos, m, 8, order, np.full(5000, 0.02), 0)
+    o = O.Tree(pos, m, 8, order, np.full(5000, 0.02), 0)
+    p_o, a_o = o.eval(0.7, targets=q)
+    p64, a64 = g._eval(q, 0.7, 3, precision="f64")
+    assert rms_rel(p64, p_o) < TOL64 and rms_rel_vec(a64, a_o) < TOL64
+    assert rms_rel(g.potentials_at_points(q, 0.7), p_o) < TOL32
+    assert rms_rel_vec(g.accelerations_at_points(q, 0.7), a_o) < TOL32
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("hmode", ["const", "var"])
+def test_softened_tree_matches_oracle(kernel, hmode):
+    n = 8000
+    pos, m, h = nfw_disc(n, seed=31)
+    if hmode == "const":
+        h = np.full(n, 0.01)
+    else:
+        h = h * np.random.default_rng(7).uniform(1.0, 30.0, n)
+    g = R().Octree(pos, m, 8, 3, h, kernel)
+    o = O.Tree(pos, m, 8, 3, h, kernel)
+    assert_same_topology(g, o)
+    assert_same_payload(g, o)
+    p_o, a_o = o.eval(0.7)
+    p64, a64 = g._eval(None, 0.7, 3, precision="f64")
+    assert rms_rel(p64, p_o) < TOL64 and rms_rel_vec(a64, a_o) < TOL64
+    p32, a32 = g._eval(None, 0.7, 3)
+    assert rms_rel(p32, p_o) < TOL32 and rms_rel_vec(a32, a_o) < TOL32
+    q, _ = plummer(500, seed=8, a=0.2)
+    p_o, a_o = o.eval(0.7, targets=q)
+    p32, a32 = g._eval(q, 0.7, 3)
+    assert rms_rel(p32, p_o) < TOL32 and rms_rel_vec(a32, a_o) < TOL32
+
+
+def test_reference_property_theta0_tree_equals_direct():
+    # gravity_tests.rs:57-126 on the GPU path (float64 mode, the reference's 1e-10 bound)
+    r = R()
+    pos, m = uniform_cube(256, 1)
+    g = r.Octree(pos, m, 32, 2)
+    p, a = g._eval(None, 0.0, 3, precision="f64")
+    p_d, a_d = O.direct(pos, m)
+    assert np.abs(p - p_d).max() < 1e-10 and np.abs(a - a_d).max() < 1e-10
+    q, _ = uniform_cube(128, 13, with_masses=False)
+    src, ms = uniform_cube(512, 11)
+    g = r.Octree(src, ms, 32, 2)
+    p, a = g._eval(q, 0.0, 3, precision="f64")
+    p_d, a_d = O.direct(src, ms, targets=q)
+    assert np.abs(p - p_d).max() < 1e-10 and np.abs(a - a_d).max() < 1e-10
+
+
+def test_reference_property_error_decreases_with_order():
+    # gravity_tests.rs:128-202 on the GPU path
+    r = R()
+    pos, m = uniform_cube(800, 21)
+    p_ref, a_ref = O.direct(pos, m)
+    ea, ep = [], []
+    for order in (0, 3, 4, 5):
+        a = r.Octree(pos, m, 64, order).compute_accelerations(0.7)
+        ea.append(np.sqrt(((a - a_ref) ** 2).sum(1).mean()))
+    for order in (0, 2, 3, 4, 5):
+        p = r.Octree(pos, m, 64, order).compute_potentials(0.7)
+        ep.append(np.sqrt(((p - p_ref) ** 2).mean()))
+    assert all(ea[i] <= ea[i - 1] for i in range(1, len(ea))) and ea[-1] <= 0.8 * ea[0]
+    assert all(ep[i] <= ep[i - 1] for i in range(1, len(ep)))
+
+
+def test_setters_follow_reference_semantics():
+    # set_softenings does not rebuild hmax (tree.rs:777-782); set_kernel switches leaf sums + gate factor
+    r = R()
+    pos, m = plummer(3000, seed=41)
+    h0 = np.full(3000, 0.05)
+    g = r.Octree(pos, m, 8, 3, h0, 0)
+    o = O.Tree(pos, m, 8, 3, h0, 0)
+    h1 = np.random.default_rng(1).uniform(0.0, 0.3, 3000)
+    g.set_softenings(h1); o.set_softenings(h1)
+    g.set_kernel(1); o.set_kernel(1)
+    p_o, a_o = o.eval(0.7)
+    p, a = g._eval(None, 0.7, 3, precision="f64")
+    assert rms_rel(p, p_o) < TOL64 and rms_rel_vec(a, a_o) < TOL64
+    g.set_softenings(None); o.set_softenings(None)
+    p_o, _ = o.eval(0.7, want=1)
+    assert rms_rel(g._eval(None, 0.7, 1, precision="f64")[0], p_o) < TOL64
+    m2 = m * np.random.default_rng(2).uniform(0.5, 2.0, 3000)
+    g.build_mass(m2); o.build_mass(m2)
+    assert_same_payload(g, o)
+
+
+def test_shard_eval_equals_full_eval():
+    r = R()
+    pos, m = hernquist(10000, seed=51)
+    g = r.Octree(pos, m, 8, 3)
+    p_full, a_full = g._eval(None, 0.7, 3)
+    for lo, hi in ((0, 2500), (2500, 7001), (7001, 10000)):
+        p, a = g._eval(None, 0.7, 3, tgt_begin=lo, count=hi - lo)
+        assert np.array_equal(p, p_full[lo:hi]) and np.array_equal(a, a_full[lo:hi])
+
+
+def test_gravity_api_tree_path_and_cache_semantics():
+    from pynbodyext.gravity import Gravity, KernelKind
+    pos, m = plummer(4000, seed=61)
+    g = Gravity(pos, m, softening=0.01, kernel=KernelKind.Spline, leaf_capacity=16, multipole_order=2)
+    # tree_* use their own defaults (8, 3): a throw-away tree, not the cached (16, 2) one
+    p = g.tree_potentials(theta=0.6)
+    assert g._tree is None
+    o = O.Tree(pos, m, 8, 3, np.full(4000, 0.01), 1)
+    assert rms_rel(p, o.eval(0.6, want=1)[0]) < TOL32
+    p2 = g.tree_potentials(theta=0.6, leaf_capacity=16, multipole_order=2)
+    assert g._tree is not None
+    o2 = O.Tree(pos, m, 16, 2, np.full(4000, 0.01), 1)
+    assert rms_rel(p2, o2.eval(0.6, want=1)[0]) < TOL32
+    a = g.tree_accelerations(positions=pos[:100] + 0.01, theta=0.7)
+    a_o = O.Tree(pos, m, 8, 3, np.full(4000, 0.01), 1).eval(0.7, targets=pos[:100] + 0.01, want=2)[1]
+    assert rms_rel_vec(a, a_o) < TOL32
+
+
+def test_bench_gravity_shape_config():
+    # benchmarks/bench_gravity.py:148-159: theta 0.7, softening 0.001, kernel=1, order 3, leaf 8, construct + potentials
+    from pynbodyext.gravity import Gravity
+    pos, m = hernquist(15682, seed=71)  # size of halo 0 of subhalo_103 (tests/conftest.py:52)
+    g = Gravity(pos, m, softening=0.001, kernel=1, leaf_capacity=8, multipole_order=3)
+    p = g.tree_potentials(theta=0.7, leaf_capacity=8, multipole_order=3, kernel=1)
+    o = O.Tree(pos, m, 8, 3, np.full(len(m), 0.001), 1)
+    assert rms_rel(p, o.eval(0.7, want=1)[0]) < TOL32
+
+
+def test_larger_tree_1e5_subsample_against_oracle():
+    pos, m = plummer(100_000, seed=1)
+    g = R().Octree(pos, m, 8, 3)
+    o = O.Tree(pos, m, 8, 3)
+    assert_same_topology(g, o)
+    assert_same_payload(g, o)
+    p_o, a_o = o.eval(0.7)
+    p, a = g._eval(None, 0.7, 3)
+    assert rms_rel(p, p_o) < TOL32 and rms_rel_vec(a, a_o) < TOL32
+    assert np.abs((p - p_o) / p_o).max() < 1e-4
