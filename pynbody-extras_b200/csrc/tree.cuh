@@ -47,7 +47,7 @@ struct pnbx_tree_impl {
     // sorted copies used by payload builds and the walk
     DevBuf<double> spos;               // (n,3) float64
     DevBuf<double> smass, sh;          // float64 (smass only if has_mass, sh only if has_h)
-    DevBuf<float4> src32;              // (x-cx, y-cy, z-cz, m) float32 relative to the root centre
+    DevBuf<float4> src32;              // (x, y, z, m) float32, relative to the COM of the particle's leaf
     DevBuf<float> sh32;
 
     // nodes, reference numbering

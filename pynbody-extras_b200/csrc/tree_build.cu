@@ -263,16 +263,27 @@ __global__ void invert_perm(const uint32_t* __restrict__ perm, int64_t n, uint32
 
 // ---- sorted copies
 __global__ void gather_sources(const double* __restrict__ pos, const double* __restrict__ mass,
-                               const uint32_t* __restrict__ perm, int64_t n, double cx, double cy, double cz,
-                               double* __restrict__ spos, double* __restrict__ smass, float4* __restrict__ src32) {
+                               const uint32_t* __restrict__ perm, int64_t n, double* __restrict__ spos,
+                               double* __restrict__ smass) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const uint32_t i = perm[s];
     const double x = pos[3 * (int64_t)i], y = pos[3 * (int64_t)i + 1], z = pos[3 * (int64_t)i + 2];
     spos[3 * s] = x; spos[3 * s + 1] = y; spos[3 * s + 2] = z;
-    const double m = mass ? mass[i] : 1.0;
-    if (smass) smass[s] = m;
-    src32[s] = make_float4((float)(x - cx), (float)(y - cy), (float)(z - cz), (float)m);
+    if (smass) smass[s] = mass[i];
+}
+// fp32 walk sources: every leaf's particles relative to that leaf's centre of mass (float64 subtraction,
+// then the cast), so close pairs keep their separation wherever the leaf sits in the box.
+__global__ void leaf_local_sources(const uint8_t* __restrict__ nchild, const uint32_t* __restrict__ start,
+                                   const uint32_t* __restrict__ count, const double* __restrict__ ncom,
+                                   const double* __restrict__ spos, const double* __restrict__ smass, int64_t nn,
+                                   float4* __restrict__ src32) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nn || nchild[i] != 0) return;
+    const double cx = ncom[3 * i], cy = ncom[3 * i + 1], cz = ncom[3 * i + 2];
+    for (uint32_t s = start[i]; s < start[i] + count[i]; ++s)
+        src32[s] = make_float4((float)(spos[3 * (int64_t)s] - cx), (float)(spos[3 * (int64_t)s + 1] - cy),
+                               (float)(spos[3 * (int64_t)s + 2] - cz), smass ? (float)smass[s] : 1.0f);
 }
 __global__ void gather_soft(const double* __restrict__ h, const uint32_t* __restrict__ perm, int64_t n,
                             double* __restrict__ sh, float* __restrict__ sh32) {
@@ -551,14 +562,10 @@ bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const DevBuf<double>& roo
 void gather_sorted_sources(pnbx_tree_impl& t, cudaStream_t s) {
     const int64_t n = t.n;
     if (n == 0) return;
-    if (!t.spos.p) {
-        t.spos.alloc((size_t)3 * n, s);
-        t.src32.alloc((size_t)n, s);
-    }
+    if (!t.spos.p) t.spos.alloc((size_t)3 * n, s);
     if (t.has_mass && !t.smass.p) t.smass.alloc((size_t)n, s);
-    PNBX_LAUNCH(gather_sources, nblk(n), 256, 0, s, t.pos.p, t.has_mass ? t.mass.p : nullptr, t.perm.p, n,
-                t.root_center[0], t.root_center[1], t.root_center[2], t.spos.p, t.has_mass ? t.smass.p : nullptr,
-                t.src32.p);
+    PNBX_LAUNCH(gather_sources, nblk(n), 256, 0, s, t.pos.p, t.has_mass ? t.mass.p : nullptr, t.perm.p, n, t.spos.p,
+                t.has_mass ? t.smass.p : nullptr);
 }
 void gather_sorted_soft(pnbx_tree_impl& t, cudaStream_t s) {
     const int64_t n = t.n;
@@ -592,6 +599,11 @@ void build_mass_payload(pnbx_tree_impl& t, cudaStream_t s, StageTimer& tm) {
     t.ctl.alloc((size_t)nn, s);
     PNBX_LAUNCH(build_walk_records, nblk(nn), 256, 0, s, t.nmass.p, t.ncom.p, t.half.p, t.node_nchild.p, t.node_start.p,
                 t.node_count.p, t.first_subnode.p, t.next_branch.p, nn, t.geom.p, t.ctl.p);
+    if (t.n > 0) {
+        if (!t.src32.p) t.src32.alloc((size_t)t.n, s);
+        PNBX_LAUNCH(leaf_local_sources, nblk(nn), 256, 0, s, t.node_nchild.p, t.node_start.p, t.node_count.p, t.ncom.p,
+                    t.spos.p, t.has_mass ? t.smass.p : nullptr, nn, t.src32.p);
+    }
     t.moments32.alloc((size_t)nn * t.n_moments, s);
     PNBX_LAUNCH(to_f32, nblk(nn * t.n_moments), 256, 0, s, t.moments.p, nn * t.n_moments, t.moments32.p);
     PNBX_CUDA(cudaGetLastError());

@@ -45,7 +45,7 @@ struct WalkArgs {
     const double* tgt;        // points: (m,3) float64
     const uint32_t* torder;   // points: walk order -> point index
     double theta2;
-    double rc[3];             // root centre (origin of the fp32 coordinates)
+    double rc[3];             // root centre (origin of the float64-mode coordinates)
     int kernel;               // PNBX_KERNEL_PLUMMER | PNBX_KERNEL_SPLINE
     double* out_pot;
     double* out_acc;
@@ -71,7 +71,7 @@ __device__ __forceinline__ T w2p_in(T u) {  // kernel.rs:108-124, u < 1
     return T(-1.0 / 15.0) / u2 + u * (T(64.0 / 3.0) + u * (T(-48.0) + u * (T(192.0 / 5.0) - T(32.0 / 3.0) * u)));
 }
 
-// source particle p in T, relative to the root centre
+// source particle p in T: float relative to its leaf's COM, double relative to the root centre
 template <class T>
 __device__ __forceinline__ Vec4T<T> load_src(const WalkArgs<T>& a, int p);
 template <>
@@ -129,10 +129,15 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
         if (c.kind >= 0) {  // leaf: always summed directly (tree.rs:1094-1112)
             if (active) {
                 T pot = T(0), ax = T(0), ay = T(0), az = T(0);
+                T lx = fx, ly = fy, lz = fz;
+                if (sizeof(T) == 4) {  // fp32 sources are stored relative to their leaf's COM
+                    const NodeGeom gl = a.geom[idx];
+                    lx = (T)(tx - gl.com[0]); ly = (T)(ty - gl.com[1]); lz = (T)(tz - gl.com[2]);
+                }
                 for (int p = c.first; p < c.first + c.kind; ++p) {
                     if (p == skip) continue;  // skip_self by index (tree.rs:130)
                     const Vec4T<T> s = load_src<T>(a, p);
-                    const T dx = s.x - fx, dy = s.y - fy, dz = s.z - fz;
+                    const T dx = s.x - lx, dy = s.y - ly, dz = s.z - lz;
                     T r2 = fma(dx, dx, fma(dy, dy, dz * dz));
                     T h = T(0);
                     if (soft) h = max(max(a.src_h[p], T(0)), th);  // tree.rs:234-235
