@@ -106,9 +106,10 @@ def cpu_reference_rate(pos, mass, target_seconds=12.0):
     n = pos.shape[0]
     h = np.full(n, EPS)
     cores = O.num_threads()
-    probe = max(cores * 2, 64)
+    probe = max(cores * 32, 1024)
+    O.direct(pos[:4096], mass[:4096], h[:4096], targets=pos[:512], kernel=0, want=2)  # spin up the OpenMP team
     t0 = time.perf_counter()
-    O.direct(pos, mass, h, targets=pos[:probe], kernel=0, want=2)
+    O.direct(pos, mass, h, targets=np.ascontiguousarray(pos[:probe]), kernel=0, want=2)
     rate = probe * n / (time.perf_counter() - t0)
     m = int(min(n, max(probe, rate * target_seconds / n)))
     m = max(cores, m - m % cores)

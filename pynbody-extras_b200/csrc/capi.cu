@@ -88,8 +88,10 @@ Exec make_exec(const pnbx_opts* opts) {
             PNBX_CUDA(cudaStreamCreateWithFlags(&ex.stream, cudaStreamNonBlocking));
             ex.own_stream = true;
         }
-        // keep freed blocks in the pool so repeated calls do not hit cudaMalloc
-        static thread_local bool pool_set[64] = {};
+    }
+    {
+        // keep freed blocks in the stream-ordered pool so repeated calls never go back to cudaMalloc
+        static bool pool_set[64] = {};
         if (dev < 64 && !pool_set[dev]) {
             cudaMemPool_t pool;
             if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {

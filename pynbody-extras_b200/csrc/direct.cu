@@ -262,6 +262,199 @@ direct_kernel(const Vec4<T>* __restrict__ src, const T* __restrict__ src_h, int6
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Packed-FP32x2 variant (Blackwell FFMA2 / FADD2 / FMUL2, `*.f32x2` PTX) for the constant-softening
+// modes. Two consecutive SOURCES share one instruction: the tile is stored as pair records
+// {x0,x1,y0,y1,z0,z1,m0,m1} (32 B), the target coordinates are duplicated once into both halves.
+// Per pair of interactions: 3 sub2 + 3 fma2 + 2 MUFU.RSQ + 3 mul2 + 3 fma2 (+1 fma2 for phi) =
+// 14 issue slots for 24 FP32-pipe lane-cycles, so the kernel is bound by the FMA pipe itself
+// (12 lane-ops per interaction) instead of by instruction issue (13 slots) — DESIGN.md §K1.
+struct alignas(32) Pair8 {
+    float x0, x1, y0, y1, z0, z1, m0, m1;
+};
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float a, float b) {
+    f2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t f2_sub(f2_t a, f2_t b) {
+    f2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
+    f2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+    f2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+constexpr int TILEP = TILE32 / 2;  // pair records per stage
+
+template <int WANT>
+__global__ void __launch_bounds__(DT, 2)
+direct_kernel_f2(const Pair8* __restrict__ src, int64_t n_src, const Vec4<float>* __restrict__ tgt, int64_t m,
+                 int64_t self_base, float eps2_const, int tiles_per_split, double* __restrict__ out_pot,
+                 double* __restrict__ out_acc) {
+    __shared__ Pair8 s_src[STAGES][TILEP];
+    __shared__ alignas(8) uint64_t s_full[STAGES];
+    const int tid = threadIdx.x;
+    const int64_t n_pairs = (n_src + 1) / 2;  // the odd tail is padded by pack_pairs (zero mass, far away)
+    const int64_t n_tiles = (n_pairs + TILEP - 1) / TILEP;
+    const int64_t tile_begin = (int64_t)blockIdx.y * tiles_per_split;
+    const int64_t tile_end = tile_begin + tiles_per_split < n_tiles ? tile_begin + tiles_per_split : n_tiles;
+    const int64_t tgt_base = (int64_t)blockIdx.x * (DT * TPT);
+
+    f2_t xi[TPT], yi[TPT], zi[TPT];
+    float xs[TPT], ys[TPT], zs[TPT];
+    int64_t gi[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+        int64_t i = tgt_base + k * DT + tid;
+        if (i > m - 1) i = m - 1;
+        Vec4<float> t = tgt[i];
+        xs[k] = t.x; ys[k] = t.y; zs[k] = t.z;
+        xi[k] = f2_pack(t.x, t.x); yi[k] = f2_pack(t.y, t.y); zi[k] = f2_pack(t.z, t.z);
+        gi[k] = self_base >= 0 ? self_base + i : -1;
+    }
+    const f2_t e2 = f2_pack(eps2_const, eps2_const);
+    double Ax[TPT], Ay[TPT], Az[TPT], P[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) Ax[k] = Ay[k] = Az[k] = P[k] = 0.0;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t tile) {
+        int st = (int)((tile - tile_begin) % STAGES);
+        int64_t q0 = tile * TILEP;
+        int cnt = (int)(n_pairs - q0 < TILEP ? n_pairs - q0 : TILEP);
+        uint32_t bytes = (uint32_t)cnt * sizeof(Pair8);
+        mbar_expect_tx(&s_full[st], bytes);
+        bulk_g2s(&s_src[st][0], src + q0, bytes, &s_full[st]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < STAGES - 1; ++s)
+            if (tile_begin + s < tile_end) issue(tile_begin + s);
+
+    const int64_t blk_lo = self_base >= 0 ? self_base + tgt_base : INT64_MAX;
+    const int64_t blk_hi = self_base >= 0 ? blk_lo + DT * TPT : INT64_MIN;
+
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+        const int it = (int)(tile - tile_begin);
+        const int st = it % STAGES;
+        if (tid == 0 && tile + STAGES - 1 < tile_end) issue(tile + STAGES - 1);
+        mbar_wait(&s_full[st], (uint32_t)((it / STAGES) & 1));
+        const int64_t q0 = tile * TILEP;
+        const int cnt = (int)(n_pairs - q0 < TILEP ? n_pairs - q0 : TILEP);
+        const int64_t j0 = 2 * q0;
+        const bool diag = (j0 < blk_hi) && (j0 + 2 * cnt > blk_lo);
+        if (!diag && cnt == TILEP) {
+            f2_t ax[TPT], ay[TPT], az[TPT], p[TPT];
+#pragma unroll
+            for (int k = 0; k < TPT; ++k) ax[k] = ay[k] = az[k] = p[k] = 0ull;  // {+0.f, +0.f}
+#pragma unroll 4
+            for (int q = 0; q < TILEP; ++q) {
+                const ulonglong4 v = *reinterpret_cast<const ulonglong4*>(&s_src[st][q]);  // {x0x1, y0y1, z0z1, m0m1}
+#pragma unroll
+                for (int k = 0; k < TPT; ++k) {
+                    const f2_t dx = f2_sub(v.x, xi[k]), dy = f2_sub(v.y, yi[k]), dz = f2_sub(v.z, zi[k]);
+                    f2_t r2 = f2_fma(dx, dx, e2);
+                    r2 = f2_fma(dy, dy, r2);
+                    r2 = f2_fma(dz, dz, r2);
+                    float ra, rb;
+                    f2_unpack(r2, ra, rb);
+                    const f2_t rinv = f2_pack(rsqrt_fast(ra), rsqrt_fast(rb));
+                    if (WANT == PNBX_WANT_POT) {
+                        p[k] = f2_fma(v.w, rinv, p[k]);
+                    } else {
+                        const f2_t mr = f2_mul(v.w, rinv);
+                        if (WANT & PNBX_WANT_POT) p[k] = f2_fma(v.w, rinv, p[k]);
+                        const f2_t g = f2_mul(mr, f2_mul(rinv, rinv));
+                        ax[k] = f2_fma(dx, g, ax[k]);
+                        ay[k] = f2_fma(dy, g, ay[k]);
+                        az[k] = f2_fma(dz, g, az[k]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < TPT; ++k) {
+                float a, b;
+                if (WANT & PNBX_WANT_ACC) {
+                    f2_unpack(ax[k], a, b); Ax[k] += (double)a + (double)b;
+                    f2_unpack(ay[k], a, b); Ay[k] += (double)a + (double)b;
+                    f2_unpack(az[k], a, b); Az[k] += (double)a + (double)b;
+                }
+                if (WANT & PNBX_WANT_POT) { f2_unpack(p[k], a, b); P[k] -= (double)a + (double)b; }
+            }
+        } else {
+            // ragged tail and/or self-skip by index: scalar loop over the same pair records
+            float ax[TPT], ay[TPT], az[TPT], p[TPT];
+#pragma unroll
+            for (int k = 0; k < TPT; ++k) ax[k] = ay[k] = az[k] = p[k] = 0.f;
+            const int nsrc_tile = (int)((n_src - j0) < 2 * cnt ? (n_src - j0) : 2 * cnt);
+            for (int j = 0; j < nsrc_tile; ++j) {
+                const Pair8& pr = s_src[st][j >> 1];
+                Vec4<float> sj;
+                if (j & 1) { sj.x = pr.x1; sj.y = pr.y1; sj.z = pr.z1; sj.w = pr.m1; }
+                else { sj.x = pr.x0; sj.y = pr.y0; sj.z = pr.z0; sj.w = pr.m0; }
+                const int64_t gj = j0 + j;
+#pragma unroll
+                for (int k = 0; k < TPT; ++k)
+                    interact<WANT, SOFT_PLUMMER_CONST, true, float>(xs[k], ys[k], zs[k], eps2_const, sj, 0.f, gj == gi[k],
+                                                                    ax[k], ay[k], az[k], p[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < TPT; ++k) {
+                if (WANT & PNBX_WANT_ACC) { Ax[k] += (double)ax[k]; Ay[k] += (double)ay[k]; Az[k] += (double)az[k]; }
+                if (WANT & PNBX_WANT_POT) P[k] += (double)p[k];
+            }
+        }
+        __syncthreads();
+    }
+    const int64_t split_off = (int64_t)blockIdx.y * m;
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+        int64_t i = tgt_base + k * DT + tid;
+        if (i < m) {
+            if (WANT & PNBX_WANT_POT) out_pot[split_off + i] = P[k];
+            if (WANT & PNBX_WANT_ACC) {
+                double* a = out_acc + 3 * (split_off + i);
+                a[0] = Ax[k]; a[1] = Ay[k]; a[2] = Az[k];
+            }
+        }
+    }
+}
+
+// float64 (n,3) positions + mass -> pair records relative to the bbox centre; an odd tail gets a
+// zero-mass partner far away (its r^2 is huge but finite: contributes exactly 0, never NaN).
+__global__ void pack_pairs(const double* __restrict__ pos, const double* __restrict__ mass, int64_t n,
+                           const double* __restrict__ bbox6, Pair8* __restrict__ out) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * q >= n) return;
+    const double cx = (bbox6[0] + bbox6[3]) * 0.5, cy = (bbox6[1] + bbox6[4]) * 0.5, cz = (bbox6[2] + bbox6[5]) * 0.5;
+    const int64_t i0 = 2 * q, i1 = 2 * q + 1;
+    Pair8 v;
+    v.x0 = (float)(pos[3 * i0] - cx); v.y0 = (float)(pos[3 * i0 + 1] - cy); v.z0 = (float)(pos[3 * i0 + 2] - cz);
+    v.m0 = mass ? (float)mass[i0] : 1.f;
+    if (i1 < n) {
+        v.x1 = (float)(pos[3 * i1] - cx); v.y1 = (float)(pos[3 * i1 + 1] - cy); v.z1 = (float)(pos[3 * i1 + 2] - cz);
+        v.m1 = mass ? (float)mass[i1] : 1.f;
+    } else {
+        v.x1 = 1e18f; v.y1 = 1e18f; v.z1 = 1e18f; v.m1 = 0.f;
+    }
+    out[q] = v;
+}
+
 // Sum the per-split partials in split order (fixed order => run-to-run deterministic).
 __global__ void reduce_splits(const double* __restrict__ part, int64_t count, int splits, double* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -388,10 +581,15 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
         }
     }
 
-    DevBuf<Vec4<T>> src4((size_t)n, s);
-    {
-        int64_t blocks = ceil_div(n, 256);
-        PNBX_LAUNCH(pack_points<T>, (unsigned)blocks, 256, 0, s, d_pos, d_mass, n, bbox.get(), T(1), src4.get());
+    const bool use_f2 = sizeof(T) == 4 && !pair_h && !getenv("PNBX_DIRECT_SCALAR");  // packed FFMA2 path
+    DevBuf<Vec4<T>> src4;
+    DevBuf<Pair8> srcp;
+    if (use_f2) {
+        srcp.alloc((size_t)(n + 1) / 2, s);
+        PNBX_LAUNCH(pack_pairs, (unsigned)ceil_div((n + 1) / 2, 256), 256, 0, s, d_pos, d_mass, n, bbox.get(), srcp.get());
+    } else {
+        src4.alloc((size_t)n, s);
+        PNBX_LAUNCH(pack_points<T>, (unsigned)ceil_div(n, 256), 256, 0, s, d_pos, d_mass, n, bbox.get(), T(1), src4.get());
     }
     DevBuf<T> srch;
     if (pair_h) {
@@ -402,12 +600,13 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     DevBuf<Vec4<T>> tgt4;
     const Vec4<T>* tgt_ptr;
     const T* tgt_h_ptr = nullptr;
-    if (self) {
+    if (self && !use_f2) {
         tgt_ptr = src4.get() + tgt_begin;
         if (pair_h) tgt_h_ptr = srch.get() + tgt_begin;
     } else {
         tgt4.alloc((size_t)m, s);
-        PNBX_LAUNCH(pack_points<T>, (unsigned)ceil_div(m, 256), 256, 0, s, d_tgt, nullptr, m, bbox.get(), T(0), tgt4.get());
+        const double* tp = self ? d_pos + 3 * tgt_begin : d_tgt;
+        PNBX_LAUNCH(pack_points<T>, (unsigned)ceil_div(m, 256), 256, 0, s, tp, nullptr, m, bbox.get(), T(0), tgt4.get());
         tgt_ptr = tgt4.get();
     }
     PNBX_CUDA(cudaGetLastError());
@@ -432,8 +631,18 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     }
     tm.begin("direct.kernel");
     kernel_events().begin(s);
-    launch_direct<T, TILE>(want, soft, src4.get(), srch.get(), n, tgt_ptr, tgt_h_ptr, m, self ? tgt_begin : -1, eps2,
-                           (int)splits, tiles_per_split, kp, ka, s);
+    if (use_f2) {
+        dim3 grid((unsigned)n_tb, (unsigned)splits);
+        const Pair8* sp = srcp.get();
+        const Vec4<float>* tp = reinterpret_cast<const Vec4<float>*>(tgt_ptr);
+        const int64_t sb = self ? tgt_begin : -1;
+        if (want == 1) PNBX_LAUNCH(direct_kernel_f2<1>, grid, DT, 0, s, sp, n, tp, m, sb, (float)eps2, tiles_per_split, kp, ka);
+        else if (want == 2) PNBX_LAUNCH(direct_kernel_f2<2>, grid, DT, 0, s, sp, n, tp, m, sb, (float)eps2, tiles_per_split, kp, ka);
+        else PNBX_LAUNCH(direct_kernel_f2<3>, grid, DT, 0, s, sp, n, tp, m, sb, (float)eps2, tiles_per_split, kp, ka);
+    } else {
+        launch_direct<T, TILE>(want, soft, src4.get(), srch.get(), n, tgt_ptr, tgt_h_ptr, m, self ? tgt_begin : -1, eps2,
+                               (int)splits, tiles_per_split, kp, ka, s);
+    }
     kernel_events().end(s);
     PNBX_CUDA(cudaGetLastError());
     if (splits > 1) {
