@@ -298,7 +298,7 @@ __device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
 
 constexpr int TILEP = TILE32 / 2;  // pair records per stage
 
-template <int WANT>
+template <int WANT, bool ALLFMA>
 __global__ void __launch_bounds__(DT, 2)
 direct_kernel_f2(const Pair8* __restrict__ src, int64_t n_src, const Vec4<float>* __restrict__ tgt, int64_t m,
                  int64_t self_base, float eps2_const, int tiles_per_split, double* __restrict__ out_pot,
@@ -325,6 +325,12 @@ direct_kernel_f2(const Pair8* __restrict__ src, int64_t n_src, const Vec4<float>
         gi[k] = self_base >= 0 ? self_base + i : -1;
     }
     const f2_t e2 = f2_pack(eps2_const, eps2_const);
+    // ALLFMA: issue the subtractions and multiplications as FFMA2 too (s*1 + (-x), a*b + (-0)): bit-identical
+    // results, but every packed op then goes down the same full-rate path.
+    const f2_t one2 = f2_pack(1.f, 1.f), nz2 = f2_pack(-0.f, -0.f);
+    f2_t nxi[TPT], nyi[TPT], nzi[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) { nxi[k] = f2_pack(-xs[k], -xs[k]); nyi[k] = f2_pack(-ys[k], -ys[k]); nzi[k] = f2_pack(-zs[k], -zs[k]); }
     double Ax[TPT], Ay[TPT], Az[TPT], P[TPT];
 #pragma unroll
     for (int k = 0; k < TPT; ++k) Ax[k] = Ay[k] = Az[k] = P[k] = 0.0;
@@ -367,7 +373,9 @@ direct_kernel_f2(const Pair8* __restrict__ src, int64_t n_src, const Vec4<float>
                 const ulonglong4 v = *reinterpret_cast<const ulonglong4*>(&s_src[st][q]);  // {x0x1, y0y1, z0z1, m0m1}
 #pragma unroll
                 for (int k = 0; k < TPT; ++k) {
-                    const f2_t dx = f2_sub(v.x, xi[k]), dy = f2_sub(v.y, yi[k]), dz = f2_sub(v.z, zi[k]);
+                    const f2_t dx = ALLFMA ? f2_fma(v.x, one2, nxi[k]) : f2_sub(v.x, xi[k]);
+                    const f2_t dy = ALLFMA ? f2_fma(v.y, one2, nyi[k]) : f2_sub(v.y, yi[k]);
+                    const f2_t dz = ALLFMA ? f2_fma(v.z, one2, nzi[k]) : f2_sub(v.z, zi[k]);
                     f2_t r2 = f2_fma(dx, dx, e2);
                     r2 = f2_fma(dy, dy, r2);
                     r2 = f2_fma(dz, dz, r2);
@@ -377,9 +385,10 @@ direct_kernel_f2(const Pair8* __restrict__ src, int64_t n_src, const Vec4<float>
                     if (WANT == PNBX_WANT_POT) {
                         p[k] = f2_fma(v.w, rinv, p[k]);
                     } else {
-                        const f2_t mr = f2_mul(v.w, rinv);
+                        const f2_t mr = ALLFMA ? f2_fma(v.w, rinv, nz2) : f2_mul(v.w, rinv);
                         if (WANT & PNBX_WANT_POT) p[k] = f2_fma(v.w, rinv, p[k]);
-                        const f2_t g = f2_mul(mr, f2_mul(rinv, rinv));
+                        const f2_t rr = ALLFMA ? f2_fma(rinv, rinv, nz2) : f2_mul(rinv, rinv);
+                        const f2_t g = ALLFMA ? f2_fma(mr, rr, nz2) : f2_mul(mr, rr);
                         ax[k] = f2_fma(dx, g, ax[k]);
                         ay[k] = f2_fma(dy, g, ay[k]);
                         az[k] = f2_fma(dz, g, az[k]);
@@ -636,9 +645,14 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
         const Pair8* sp = srcp.get();
         const Vec4<float>* tp = reinterpret_cast<const Vec4<float>*>(tgt_ptr);
         const int64_t sb = self ? tgt_begin : -1;
-        if (want == 1) PNBX_LAUNCH(direct_kernel_f2<1>, grid, DT, 0, s, sp, n, tp, m, sb, (float)eps2, tiles_per_split, kp, ka);
-        else if (want == 2) PNBX_LAUNCH(direct_kernel_f2<2>, grid, DT, 0, s, sp, n, tp, m, sb, (float)eps2, tiles_per_split, kp, ka);
-        else PNBX_LAUNCH(direct_kernel_f2<3>, grid, DT, 0, s, sp, n, tp, m, sb, (float)eps2, tiles_per_split, kp, ka);
+        static const bool allfma = getenv("PNBX_F2_ALLFMA") != nullptr;
+#define PNBX_F2(W)                                                                                                     \
+    if (want == W) {                                                                                                   \
+        if (allfma) PNBX_LAUNCH((direct_kernel_f2<W, true>), grid, DT, 0, s, sp, n, tp, m, sb, (float)eps2, tiles_per_split, kp, ka); \
+        else PNBX_LAUNCH((direct_kernel_f2<W, false>), grid, DT, 0, s, sp, n, tp, m, sb, (float)eps2, tiles_per_split, kp, ka);      \
+    }
+        PNBX_F2(1) PNBX_F2(2) PNBX_F2(3)
+#undef PNBX_F2
     } else {
         launch_direct<T, TILE>(want, soft, src4.get(), srch.get(), n, tgt_ptr, tgt_h_ptr, m, self ? tgt_begin : -1, eps2,
                                (int)splits, tiles_per_split, kp, ka, s);

@@ -1,6 +1,6 @@
 // peak.cu — FP32 FMA-pipe peak microbenchmark (roofline denominator for K1; BASELINE.md §2 asks
 // the builder to measure it because MEASURED_PEAKS.json has no FP32 entry).
-// variant 0: scalar FFMA chains; variant 1: packed fma.rn.f32x2 (FFMA2) chains.
+// variant 0: scalar FFMA chains; 1: packed fma.rn.f32x2 (FFMA2); 2: mul.f32x2; 3: add.f32x2 (ops counted as 2 flop each).
 #include "common.cuh"
 
 namespace pnbx {
@@ -26,7 +26,11 @@ __global__ void __launch_bounds__(256) fma_chain(float* out, int iters, float a,
         for (int c = 0; c < CHAINS / 2; ++c) asm("mov.b64 %0, {%1, %2};" : "=l"(p[c]) : "f"(x[2 * c]), "f"(x[2 * c + 1]));
         for (int i = 0; i < iters; ++i) {
 #pragma unroll
-            for (int c = 0; c < CHAINS / 2; ++c) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[c]) : "l"(ab), "l"(bb));
+            for (int c = 0; c < CHAINS / 2; ++c) {
+                if (VARIANT == 1) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[c]) : "l"(ab), "l"(bb));
+                if (VARIANT == 2) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p[c]) : "l"(ab));
+                if (VARIANT == 3) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[c]) : "l"(bb));
+            }
         }
 #pragma unroll
         for (int c = 0; c < CHAINS / 2; ++c) asm("mov.b64 {%0, %1}, %2;" : "=f"(x[2 * c]), "=f"(x[2 * c + 1]) : "l"(p[c]));
@@ -57,7 +61,9 @@ extern "C" int pnbx_measure_fp32_peak(int device, int variant, double* tflops) {
         for (int rep = 0; rep < 5; ++rep) {
             PNBX_CUDA(cudaEventRecord(a, ex.stream));
             if (variant == 0) fma_chain<0><<<grid, 256, 0, ex.stream>>>(out.get(), iters, 0.999f, 1e-3f);
-            else fma_chain<1><<<grid, 256, 0, ex.stream>>>(out.get(), iters, 0.999f, 1e-3f);
+            else if (variant == 1) fma_chain<1><<<grid, 256, 0, ex.stream>>>(out.get(), iters, 0.999f, 1e-3f);
+            else if (variant == 2) fma_chain<2><<<grid, 256, 0, ex.stream>>>(out.get(), iters, 0.999f, 1e-3f);
+            else fma_chain<3><<<grid, 256, 0, ex.stream>>>(out.get(), iters, 0.999f, 1e-3f);
             PNBX_CUDA(cudaEventRecord(b, ex.stream));
             PNBX_CUDA(cudaEventSynchronize(b));
             float ms = 0.f;
