@@ -153,6 +153,89 @@ __device__ inline void m2m_accumulate(double* acc, const double* child, int orde
     }
 }
 
+// Compile-time-order variants: with ORDER a template parameter every loop below unrolls, the tables
+// fold to constants, moments live in registers and the only true divisions left are by 6, 12, 24, ...
+// (division by 1, 2, 4 is exact, so it is issued as a multiplication). Same operation order, same bits.
+template <int NC>
+__device__ __forceinline__ void p2m_accumulate_ct(double (&mom)[NC], double mass, double x, double y, double z) {
+    double pw[3][6];
+    const double v[3] = {x, y, z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        pw[a][1] = v[a];
+        pw[a][2] = __dmul_rn(v[a], v[a]);
+        pw[a][3] = __dmul_rn(v[a], pw[a][2]);
+        pw[a][4] = __dmul_rn(pw[a][2], pw[a][2]);
+        pw[a][5] = __dmul_rn(v[a], pw[a][4]);
+    }
+    mom[0] = __dadd_rn(mom[0], mass);
+#pragma unroll
+    for (int i = 1; i < NC; ++i) {
+        double t = __dmul_rn(kP2M[i].c, mass);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int tok = kP2M[i].tok[k];
+            if (tok != 0) t = __dmul_rn(t, pw[tok >> 3][tok & 7]);
+        }
+        mom[i] = __dadd_rn(mom[i], t);
+    }
+}
+
+__host__ __device__ constexpr int lmn_index_ct(int l, int m, int n) {
+    const int o = l + m + n;
+    const int lo = o == 0 ? 0 : o == 1 ? 1 : o == 2 ? 4 : o == 3 ? 10 : o == 4 ? 20 : 35;
+    const int hi = o == 0 ? 1 : o == 1 ? 4 : o == 2 ? 10 : o == 3 ? 20 : o == 4 ? 35 : 56;
+    for (int i = lo; i < hi; ++i)
+        if (kLmn[i].l == l && kLmn[i].m == m) return i;
+    return -1;
+}
+__host__ __device__ constexpr bool is_pow2_small(int d) { return d == 1 || d == 2 || d == 4 || d == 8 || d == 16; }
+
+template <int ORDER, int NC>
+__device__ __forceinline__ void m2m_accumulate_ct(double (&acc)[NC], const double* __restrict__ child,
+                                                  const double shift[3]) {
+    constexpr int fact[6] = {1, 1, 2, 6, 24, 120};
+    double spw[3][6];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        spw[a][0] = 1.0;
+        spw[a][1] = shift[a];
+        spw[a][2] = __dmul_rn(shift[a], shift[a]);
+        spw[a][3] = __dmul_rn(shift[a], spw[a][2]);
+        spw[a][4] = __dmul_rn(spw[a][2], spw[a][2]);
+        spw[a][5] = __dmul_rn(shift[a], spw[a][4]);
+    }
+    double ch[NC];
+#pragma unroll
+    for (int t = 0; t < NC; ++t) ch[t] = child[t];
+#pragma unroll
+    for (int t = 0; t < NC; ++t) {
+        const int l = kLmn[t].l, m = kLmn[t].m, n = kLmn[t].n;
+        if (l + m + n <= ORDER) {
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i <= 5; ++i)
+#pragma unroll
+                for (int j = 0; j <= 5; ++j)
+#pragma unroll
+                    for (int k = 0; k <= 5; ++k) {
+                        if (i <= l && j <= m && k <= n) {
+                            const double base = ch[lmn_index_ct(i, j, k)];
+                            const int dl = l - i, dm = m - j, dn = n - k;
+                            // pow = sx*sy*sz (1.0 factors are exact identities), coeff = sign*pow/(dl! dm! dn!)
+                            double pw = (dl + dm + dn == 0) ? 1.0 : __dmul_rn(__dmul_rn(spw[0][dl], spw[1][dm]), spw[2][dn]);
+                            if ((dl + dm + dn) & 1) pw = -pw;
+                            const int den = fact[dl] * fact[dm] * fact[dn];
+                            const double coeff = is_pow2_small(den) ? __dmul_rn(pw, 1.0 / den) : __ddiv_rn(pw, (double)den);
+                            const double term = __dmul_rn(coeff, base);
+                            sum = (base == 0.0) ? sum : __dadd_rn(sum, term);  // the reference skips zero moments
+                        }
+                    }
+            acc[t] = __dadd_rn(acc[t], sum);
+        }
+    }
+}
+
 // ---- derivatives of 1/r and M2P ----------------------------------------------------------------
 template <class T>
 __device__ __forceinline__ T inv_sqrt(T x);
@@ -308,6 +391,81 @@ __device__ __forceinline__ void m2p_accel(const T* M, const T* D, T& ax, T& ay, 
         az -= M[I004] * D[I005] + M[I013] * D[I014] + M[I022] * D[I023] + M[I031] * D[I032] + M[I040] * D[I041] +
               M[I103] * D[I104] + M[I112] * D[I113] + M[I121] * D[I122] + M[I130] * D[I131] + M[I202] * D[I203] +
               M[I211] * D[I212] + M[I220] * D[I221] + M[I301] * D[I302] + M[I310] * D[I311] + M[I400] * D[I401];
+    }
+}
+
+// ---- fp32 fast M2P for orders <= 3 ---------------------------------------------------------------
+// Algebraically the same sums as m2p_potential / m2p_accel (D_ij = t3 u_i u_j + t2' d_ij,
+// D_ijk = t4 u_i u_j u_k + t3' (d_ij u_k + d_ik u_j + d_jk u_i), u = d/r), contracted with the moments
+// BEFORE expanding the tensors, which needs ~3x fewer instructions:
+//   phi = -M/r - (3 s - trS)/r^3 + (15 C(u) - 3 w.u)/r^4
+//   a   =  M d/r^3 + ((15 s - 3 trS) u - 6 S u)/r^4          (dipole about the COM is rounding noise: dropped)
+// with S the symmetric second-moment matrix (S_xx = m200, S_xy = m110/2, ...), s = u.S.u,
+// C(u) = sum_{l+m+n=3} M_lmn u^lmn, w_x = 3 m300 + m120 + m102 (cyclic).
+// Per-node record (float): [0] M, [1..6] 6S (xx,yy,zz,xy,xz,yz), [7] 3 trS, [8..17] octupole (field order),
+// [18..20] 3w, [21..23] pad.  REC = 1 (order<=1), 8 (order 2), 24 (order 3).
+__host__ __device__ constexpr int fast_rec_floats(int order) { return order <= 1 ? 1 : order == 2 ? 8 : 24; }
+
+template <int ORDER, int WANT>
+__device__ __forceinline__ void m2p_fast(const float* __restrict__ rec, float dx, float dy, float dz, float& pot,
+                                         float& ax, float& ay, float& az) {
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, FLT_MIN)));
+    const float ri = inv_sqrt<float>(r2);
+    const float ri2 = ri * ri, ri3 = ri2 * ri;
+    if (ORDER <= 1) {
+        const float M = __ldg(rec);
+        if (WANT & 1) pot = -M * ri;
+        if (WANT & 2) { const float g = M * ri3; ax = g * dx; ay = g * dy; az = g * dz; }
+        return;
+    }
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rec));
+    const float M = r0.x;
+    const bool need_quad = (WANT & 1) || ORDER >= 3;
+    float ux = dx * ri, uy = dy * ri, uz = dz * ri;
+    float qx = 0.f, qy = 0.f, qz = 0.f, s6 = 0.f, tr3 = 0.f;
+    if (need_quad) {
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(rec) + 1);
+        const float Sxx = r0.y, Syy = r0.z, Szz = r0.w, Sxy = r1.x, Sxz = r1.y, Syz = r1.z;
+        tr3 = r1.w;
+        qx = fmaf(Sxz, uz, fmaf(Sxy, uy, Sxx * ux));  // 6 S u
+        qy = fmaf(Syz, uz, fmaf(Syy, uy, Sxy * ux));
+        qz = fmaf(Szz, uz, fmaf(Syz, uy, Sxz * ux));
+        s6 = fmaf(qz, uz, fmaf(qy, uy, qx * ux));     // 6 u.S.u
+    }
+    if (WANT & 1) {
+        float phi = -M * ri;
+        phi = fmaf(-ri3, fmaf(0.5f, s6, -(1.f / 3.f) * tr3), phi);  // -(3 s - trS)/r^3
+        if (ORDER >= 3) {
+            const float4 r2v = __ldg(reinterpret_cast<const float4*>(rec) + 2);
+            const float4 r3v = __ldg(reinterpret_cast<const float4*>(rec) + 3);
+            const float4 r4v = __ldg(reinterpret_cast<const float4*>(rec) + 4);
+            // octupole in field order: m300 m030 m003 m210 | m201 m120 m102 m021 | m012 m111 3wx 3wy | 3wz
+            const float m300 = r2v.x, m030 = r2v.y, m003 = r2v.z, m210 = r2v.w;
+            const float m201 = r3v.x, m120 = r3v.y, m102 = r3v.z, m021 = r3v.w;
+            const float m012 = r4v.x, m111 = r4v.y, wx3 = r4v.z, wy3 = r4v.w;
+            const float wz3 = __ldg(rec + 20);
+            const float cx = fmaf(m201, uz, fmaf(m210, uy, m300 * ux));
+            const float cy = fmaf(m021, uz, fmaf(m120, ux, m030 * uy));
+            const float cz = fmaf(m012, uy, fmaf(m102, ux, m003 * uz));
+            float C = (ux * ux) * cx;
+            C = fmaf(uy * uy, cy, C);
+            C = fmaf(uz * uz, cz, C);
+            C = fmaf(m111 * ux, uy * uz, C);
+            const float wu3 = fmaf(wz3, uz, fmaf(wy3, uy, wx3 * ux));
+            phi = fmaf(ri2 * ri2, fmaf(15.f, C, -wu3), phi);
+        }
+        pot = phi;
+    }
+    if (WANT & 2) {
+        const float g = M * ri3;
+        ax = g * dx; ay = g * dy; az = g * dz;
+        if (ORDER >= 3) {
+            const float ri4 = ri2 * ri2;
+            const float c1 = fmaf(2.5f, s6, -tr3);  // 15 s - 3 trS
+            ax = fmaf(ri4, fmaf(c1, ux, -qx), ax);
+            ay = fmaf(ri4, fmaf(c1, uy, -qy), ay);
+            az = fmaf(ri4, fmaf(c1, uz, -qz), az);
+        }
     }
 }
 

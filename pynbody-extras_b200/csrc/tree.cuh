@@ -68,7 +68,8 @@ struct pnbx_tree_impl {
     DevBuf<double> nmass, ncom, hmax;  // (nn), (nn,3), (nn)
     int n_moments = 0;
     DevBuf<double> moments;            // (nn, n_moments) float64
-    DevBuf<float> moments32;           // same, float32 for the walk
+    DevBuf<float> moments32;           // fp32 walk records, rec32 floats per node (multipole.cuh: m2p_fast layout for
+    int rec32 = 0;                     // order <= 3, the plain coefficients padded to a multiple of 4 for orders 4, 5)
     DevBuf<NodeGeom> geom;
     DevBuf<NodeCtl> ctl;
 };

@@ -303,7 +303,9 @@ struct PayloadArgs {
     const double* spos; const double* smass; const double* sh;
     double* nmass; double* ncom; double* hmax; double* moments; int order; int ncoef;
 };
-__global__ void payload_level(PayloadArgs a) {
+template <int ORDER>  // effective order: 0 (monopole storage, multipole_order <= 1), 2, 3, 4, 5
+__global__ void __launch_bounds__(128) payload_level(PayloadArgs a) {
+    constexpr int NC = mp::stored_coeffs(ORDER);
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.count) return;
     const int32_t id = a.ids[j];
@@ -350,15 +352,16 @@ __global__ void payload_level(PayloadArgs a) {
     if (a.hmax) a.hmax[id] = hm;
 
     // multipoles about the node's centre of mass
-    double mom[mp::NCOEF];
-    for (int t = 0; t < a.ncoef; ++t) mom[t] = 0.0;
+    double mom[NC];
+#pragma unroll
+    for (int t = 0; t < NC; ++t) mom[t] = 0.0;
     if (mass != 0.0) {
         if (nc == 0) {
             const uint32_t s0 = a.start[id], c = a.pcount[id];
             for (uint32_t s = s0; s < s0 + c; ++s) {
                 const double m = a.smass ? a.smass[s] : 1.0;
-                mp::p2m_accumulate(mom, a.ncoef, m, __dsub_rn(a.spos[3 * (int64_t)s], cx),
-                                   __dsub_rn(a.spos[3 * (int64_t)s + 1], cy), __dsub_rn(a.spos[3 * (int64_t)s + 2], cz));
+                mp::p2m_accumulate_ct<NC>(mom, m, __dsub_rn(a.spos[3 * (int64_t)s], cx),
+                                          __dsub_rn(a.spos[3 * (int64_t)s + 1], cy), __dsub_rn(a.spos[3 * (int64_t)s + 2], cz));
             }
         } else {
             const int32_t c0 = a.first_subnode[id];
@@ -367,11 +370,12 @@ __global__ void payload_level(PayloadArgs a) {
                 if (a.nmass[c] == 0.0) continue;
                 const double shift[3] = {__dsub_rn(cx, a.ncom[3 * (int64_t)c]), __dsub_rn(cy, a.ncom[3 * (int64_t)c + 1]),
                                          __dsub_rn(cz, a.ncom[3 * (int64_t)c + 2])};
-                mp::m2m_accumulate(mom, a.moments + (int64_t)c * a.ncoef, a.order <= 1 ? 0 : a.order, a.ncoef, shift);
+                mp::m2m_accumulate_ct<ORDER, NC>(mom, a.moments + (int64_t)c * NC, shift);
             }
         }
     }
-    for (int t = 0; t < a.ncoef; ++t) a.moments[(int64_t)id * a.ncoef + t] = mom[t];
+#pragma unroll
+    for (int t = 0; t < NC; ++t) a.moments[(int64_t)id * NC + t] = mom[t];
 }
 
 __global__ void build_walk_records(const double* __restrict__ nmass, const double* __restrict__ ncom,
@@ -394,9 +398,30 @@ __global__ void build_walk_records(const double* __restrict__ nmass, const doubl
     c.pad = 0;
     ctl[i] = c;
 }
-__global__ void to_f32(const double* __restrict__ in, int64_t n, float* __restrict__ out) {
+// fp32 walk records from the float64 moments (layout: multipole.cuh, m2p_fast)
+__global__ void pack_walk_moments(const double* __restrict__ mom, int64_t nn, int order, int K, int rec,
+                                  float* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (float)in[i];
+    if (i >= nn) return;
+    const double* m = mom + i * K;
+    float* o = out + i * rec;
+    using namespace mp;
+    if (order <= 1) { o[0] = (float)m[I000]; return; }
+    if (order >= 4) {
+        for (int t = 0; t < rec; ++t) o[t] = t < K ? (float)m[t] : 0.f;
+        return;
+    }
+    o[0] = (float)m[I000];
+    o[1] = (float)(6.0 * m[I200]); o[2] = (float)(6.0 * m[I020]); o[3] = (float)(6.0 * m[I002]);
+    o[4] = (float)(3.0 * m[I110]); o[5] = (float)(3.0 * m[I101]); o[6] = (float)(3.0 * m[I011]);
+    o[7] = (float)(3.0 * (m[I200] + m[I020] + m[I002]));
+    if (order >= 3) {
+        for (int t = 0; t < 10; ++t) o[8 + t] = (float)m[I300 + t];
+        o[18] = (float)(3.0 * (3.0 * m[I300] + m[I120] + m[I102]));
+        o[19] = (float)(3.0 * (3.0 * m[I030] + m[I210] + m[I012]));
+        o[20] = (float)(3.0 * (3.0 * m[I003] + m[I201] + m[I021]));
+        o[21] = o[22] = o[23] = 0.f;
+    }
 }
 
 inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)std::max<int64_t>(1, ceil_div(n, t)); }
@@ -593,7 +618,13 @@ void build_mass_payload(pnbx_tree_impl& t, cudaStream_t s, StageTimer& tm) {
         a.spos = t.spos.p; a.smass = t.has_mass ? t.smass.p : nullptr; a.sh = t.has_h ? t.sh.p : nullptr;
         a.nmass = t.nmass.p; a.ncom = t.ncom.p; a.hmax = t.has_hmax ? t.hmax.p : nullptr; a.moments = t.moments.p;
         a.order = t.order; a.ncoef = t.n_moments;
-        PNBX_LAUNCH(payload_level, nblk(a.count, 128), 128, 0, s, a);
+        switch (t.order <= 1 ? 0 : t.order) {
+            case 0: PNBX_LAUNCH(payload_level<0>, nblk(a.count, 128), 128, 0, s, a); break;
+            case 2: PNBX_LAUNCH(payload_level<2>, nblk(a.count, 128), 128, 0, s, a); break;
+            case 3: PNBX_LAUNCH(payload_level<3>, nblk(a.count, 128), 128, 0, s, a); break;
+            case 4: PNBX_LAUNCH(payload_level<4>, nblk(a.count, 128), 128, 0, s, a); break;
+            default: PNBX_LAUNCH(payload_level<5>, nblk(a.count, 128), 128, 0, s, a); break;
+        }
     }
     t.geom.alloc((size_t)nn, s);
     t.ctl.alloc((size_t)nn, s);
@@ -604,8 +635,9 @@ void build_mass_payload(pnbx_tree_impl& t, cudaStream_t s, StageTimer& tm) {
         PNBX_LAUNCH(leaf_local_sources, nblk(nn), 256, 0, s, t.node_nchild.p, t.node_start.p, t.node_count.p, t.ncom.p,
                     t.spos.p, t.has_mass ? t.smass.p : nullptr, nn, t.src32.p);
     }
-    t.moments32.alloc((size_t)nn * t.n_moments, s);
-    PNBX_LAUNCH(to_f32, nblk(nn * t.n_moments), 256, 0, s, t.moments.p, nn * t.n_moments, t.moments32.p);
+    t.rec32 = t.order <= 3 ? mp::fast_rec_floats(t.order) : (t.n_moments + 3) / 4 * 4;
+    t.moments32.alloc((size_t)nn * t.rec32, s);
+    PNBX_LAUNCH(pack_walk_moments, nblk(nn), 256, 0, s, t.moments.p, nn, t.order, t.n_moments, t.rec32, t.moments32.p);
     PNBX_CUDA(cudaGetLastError());
     t.has_payload = true;
     tm.end();

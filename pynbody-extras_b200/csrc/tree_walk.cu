@@ -29,7 +29,7 @@ struct WalkArgs {
     const NodeGeom* geom;
     const NodeCtl* ctl;
     const double* hmax;   // nullable
-    const T* moments;     // (nn, K)
+    const T* moments;     // (nn, K): float64 coefficients (T=double) or fp32 walk records (T=float)
     int K;
     const void* src;      // float4 (T=float) or double spos/smass (T=double)
     const double* spos;   // sorted float64 positions
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
     int idx = __ballot_sync(FULL, valid) ? 0 : -1;
     while (idx >= 0) {
         const NodeCtl c = a.ctl[idx];
+        const NodeGeom gm = a.geom[idx];  // issued together with ctl: one memory round trip per visit
         if (!active && resume == idx) active = true;
         if (c.kind == -2) {  // zero mass: skip the subtree (tree.rs:1087-1090)
             idx = c.next_branch;
@@ -131,8 +132,7 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
                 T pot = T(0), ax = T(0), ay = T(0), az = T(0);
                 T lx = fx, ly = fy, lz = fz;
                 if (sizeof(T) == 4) {  // fp32 sources are stored relative to their leaf's COM
-                    const NodeGeom gl = a.geom[idx];
-                    lx = (T)(tx - gl.com[0]); ly = (T)(ty - gl.com[1]); lz = (T)(tz - gl.com[2]);
+                    lx = (T)(tx - gm.com[0]); ly = (T)(ty - gm.com[1]); lz = (T)(tz - gm.com[2]);
                 }
                 for (int p = c.first; p < c.first + c.kind; ++p) {
                     if (p == skip) continue;  // skip_self by index (tree.rs:130)
@@ -169,7 +169,6 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
             continue;
         }
         // ---- internal node: per-lane opening decision in float64 (tree.rs:1114-1126)
-        const NodeGeom gm = a.geom[idx];
         bool accept = false;
         double dx = 0, dy = 0, dz = 0;
         if (active) {
@@ -190,26 +189,47 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
         }
         const unsigned need_open = __ballot_sync(FULL, active && !accept);
         if (active && accept) {
-            const T* M = a.moments + (int64_t)idx * a.K;
-            T D[mp::NCOEF];
-            mp::derivatives<DORD, T>((T)dx, (T)dy, (T)dz, tiny_v<T>(), D);
-            if (ORDER <= 1) {
-                const T m0 = M[0];
-                if (WANT & PNBX_WANT_POT) P += (double)(-m0 * D[mp::I000]);
-                if (WANT & PNBX_WANT_ACC) {
-                    Ax += (double)(-m0 * D[mp::I100]);
-                    Ay += (double)(-m0 * D[mp::I010]);
-                    Az += (double)(-m0 * D[mp::I001]);
-                }
+            if (sizeof(T) == 4 && ORDER <= 3) {
+                // fp32, order <= 3: contracted closed forms (multipole.cuh m2p_fast)
+                float pot = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+                mp::m2p_fast<ORDER, WANT>(reinterpret_cast<const float*>(a.moments) + (int64_t)idx * a.K, (float)dx, (float)dy,
+                                          (float)dz, pot, ax, ay, az);
+                if (WANT & PNBX_WANT_POT) P += (double)pot;
+                if (WANT & PNBX_WANT_ACC) { Ax += (double)ax; Ay += (double)ay; Az += (double)az; }
             } else {
-                T Mr[mp::stored_coeffs(ORDER)];
+                const T* M = a.moments + (int64_t)idx * a.K;
+                T D[mp::NCOEF];
+                mp::derivatives<DORD, T>((T)dx, (T)dy, (T)dz, tiny_v<T>(), D);
+                if (ORDER <= 1) {
+                    const T m0 = M[0];
+                    if (WANT & PNBX_WANT_POT) P += (double)(-m0 * D[mp::I000]);
+                    if (WANT & PNBX_WANT_ACC) {
+                        Ax += (double)(-m0 * D[mp::I100]);
+                        Ay += (double)(-m0 * D[mp::I010]);
+                        Az += (double)(-m0 * D[mp::I001]);
+                    }
+                } else {
+                    T Mr[mp::stored_coeffs(ORDER)];
+                    if (sizeof(T) == 4) {  // padded to a multiple of 4 floats: vector loads
+                        constexpr int NV = (mp::stored_coeffs(ORDER) + 3) / 4;
 #pragma unroll
-                for (int i = 0; i < mp::stored_coeffs(ORDER); ++i) Mr[i] = M[i];
-                if (WANT & PNBX_WANT_POT) P += (double)mp::m2p_potential<ORDER, T>(Mr, D);
-                if (WANT & PNBX_WANT_ACC) {
-                    T ax, ay, az;
-                    mp::m2p_accel<ORDER, T>(Mr, D, ax, ay, az);
-                    Ax += (double)ax; Ay += (double)ay; Az += (double)az;
+                        for (int v = 0; v < NV; ++v) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(M) + v);
+                            const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (4 * v + e < mp::stored_coeffs(ORDER)) Mr[4 * v + e] = (T)qq[e];
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < mp::stored_coeffs(ORDER); ++i) Mr[i] = M[i];
+                    }
+                    if (WANT & PNBX_WANT_POT) P += (double)mp::m2p_potential<ORDER, T>(Mr, D);
+                    if (WANT & PNBX_WANT_ACC) {
+                        T ax, ay, az;
+                        mp::m2p_accel<ORDER, T>(Mr, D, ax, ay, az);
+                        Ax += (double)ax; Ay += (double)ay; Az += (double)az;
+                    }
                 }
             }
         }
@@ -317,7 +337,6 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
     auto fill = [&](auto& a) {
         a.geom = t.geom.p; a.ctl = t.ctl.p;
         a.hmax = t.has_hmax ? t.hmax.p : nullptr;
-        a.K = t.n_moments;
         a.spos = t.spos.p; a.smass = t.has_mass ? t.smass.p : nullptr;
         a.sh = t.has_h ? t.sh.p : nullptr;
         a.perm = t.perm.p;
@@ -334,12 +353,12 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
     if (ex.f64) {
         WalkArgs<double> a;
         fill(a);
-        a.moments = t.moments.p; a.src = nullptr; a.src_h = t.has_h ? t.sh.p : nullptr;
+        a.moments = t.moments.p; a.K = t.n_moments; a.src = nullptr; a.src_h = t.has_h ? t.sh.p : nullptr;
         launch_walk<double>(order, want, a, s);
     } else {
         WalkArgs<float> a;
         fill(a);
-        a.moments = t.moments32.p; a.src = t.src32.p; a.src_h = t.has_h ? t.sh32.p : nullptr;
+        a.moments = t.moments32.p; a.K = t.rec32; a.src = t.src32.p; a.src_h = t.has_h ? t.sh32.p : nullptr;
         launch_walk<float>(order, want, a, s);
     }
     kernel_events().end(s);
