@@ -122,6 +122,117 @@ def cpu_reference_rate(pos, mass, target_seconds=12.0):
     return m * n / dt, cores, f"{m} of {n} targets (evenly strided), all {n} sources, at-points kernel path, {dt:.1f} s"
 
 
+def tree_section(args, rank, world, local, dev, barrier, peak_tf):
+    """Secondary metric of BASELINE.json: tree gravity particles/s on config 3 (NFW halo + exponential disc,
+    per-particle spline softening, theta 0.7, order 3, leaf 8; bench_gravity.py shape = construct + potentials).
+    Sources replicated on every rank (same seed), targets sharded; every rank builds the identical tree."""
+    import torch
+    import torch.distributed as dist
+
+    from benchmarks.synthetic import nfw_disc
+    from pynbodyext.gravity import Gravity, KernelKind
+    from pynbodyext.gravity import device as gdev
+    from pynbodyext.gravity.sharded import shard_bounds
+
+    n, theta, order, leaf = args.tree_n, 0.7, 3, 8
+    pos, mass, h = nfw_disc(n, seed=3)
+    b = shard_bounds(n, world)
+    lo, hi = b[rank], b[rank + 1]
+    d_pos, d_mass, d_h = (torch.from_numpy(a).to(dev) for a in (pos, mass, h))
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps):
+        out = []
+        for _ in range(reps):
+            barrier()
+            e0, e1 = ev(), ev()
+            e0.record()
+            r = fn()
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out.append(float(t[0]))
+        return min(out), r
+
+    for _ in range(2):  # warm the memory pool
+        t = gdev.OctreeDevice(d_pos, d_mass, leaf, order, d_h, 1)
+        t.eval(theta, 1, tgt_begin=lo, count=hi - lo)
+        del t
+    build_ms, tree = timed(lambda: gdev.OctreeDevice(d_pos, d_mass, leaf, order, d_h, 1), args.steps)
+    walk_pot_ms, _ = timed(lambda: tree.eval(theta, 1, tgt_begin=lo, count=hi - lo, kernel_events=True), args.steps)
+    k_pot_ms = gdev.last_kernel_ms()
+    walk_acc_ms, _ = timed(lambda: tree.eval(theta, 2, tgt_begin=lo, count=hi - lo, kernel_events=True), args.steps)
+    k_acc_ms = gdev.last_kernel_ms()
+
+    def construct_and_pot():
+        tt = gdev.OctreeDevice(d_pos, d_mass, leaf, order, d_h, 1)
+        return tt.eval(theta, 1, tgt_begin=lo, count=hi - lo)
+
+    both_ms, _ = timed(construct_and_pot, args.steps)
+    cnt = tree.walk_counters(theta, tgt_begin=lo, count=hi - lo)
+    info = tree.info()
+    m_t = hi - lo
+    flop_acc = cnt["accepts"] * 140.0 + cnt["leaf_particles"] * 20.0 + cnt["visits"] * 10.0
+    flop_pot = cnt["accepts"] * 120.0 + cnt["leaf_particles"] * 20.0 + cnt["visits"] * 10.0
+    res = {
+        "workload": f"NFW halo (c=10) + exponential disc N={n}, seed 3, per-particle spline softening, theta={theta}, "
+                    f"multipole_order={order}, leaf_capacity={leaf} (BASELINE.json configs[2])",
+        "metric": "tree_particles_per_s (construct + potentials, device-resident, bench_gravity.py shape)",
+        "value": n / (both_ms * 1e-3), "unit": "particles/s", "n_gpus": world,
+        "construct_ms": build_ms, "walk_pot_ms": walk_pot_ms, "walk_acc_ms": walk_acc_ms,
+        "construct_plus_pot_ms": both_ms,
+        "walk_only_particles_per_s": {"pot": n / (walk_pot_ms * 1e-3), "acc": n / (walk_acc_ms * 1e-3)},
+        "nodes": info["n_nodes"], "depth": info["depth"],
+        "per_target": {k: v / m_t for k, v in cnt.items()},
+        "roofline_walk": {
+            "bound": "fp32", "kernel": "walk_kernel<3,acc,f32>", "unit": "TFLOP/s",
+            "achieved": flop_acc / (k_acc_ms * 1e-3) / 1e12, "peak": peak_tf,
+            "frac": flop_acc / (k_acc_ms * 1e-3) / 1e12 / peak_tf, "kernel_ms": k_acc_ms,
+            "achieved_pot": flop_pot / (k_pot_ms * 1e-3) / 1e12, "kernel_ms_pot": k_pot_ms,
+            "work_model": "accepts*140(acc)|120(pot) + leaf_pairs*20 + visits*10 flop (BASELINE.md §3), counts from "
+                          "pnbx_tree_walk_counters (== oracle counters)",
+            "interactions_per_s": (cnt["accepts"] + cnt["leaf_particles"]) / (k_acc_ms * 1e-3),
+        },
+        "roofline_build": {
+            "bound": "hbm", "unit": "GB/s", "achieved": 0.53e3 * n / (build_ms * 1e-3) / 1e9,
+            "peak": peaks().get("hbm_gbs", 6650.0), "traffic": None,
+            "frac": 0.53e3 * n / (build_ms * 1e-3) / 1e9 / peaks().get("hbm_gbs", 6650.0),
+            "algorithmic_bytes_per_particle": 530,
+        },
+    }
+    if rank == 0 and world == 1:
+        # e2e through the drop-in API with host arrays (H2D of 40 B/particle and D2H inside the timed region)
+        g = Gravity(pos, mass, softening=h, kernel=KernelKind.Spline)
+        g.tree_potentials(theta=theta)
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            g2 = Gravity(pos, mass, softening=h, kernel=KernelKind.Spline)
+            out = g2.tree_potentials(theta=theta)
+        dt = (time.perf_counter() - t0) / reps
+        res["e2e"] = {"value": n / dt, "unit": "particles/s", "ms_per_step": dt * 1e3,
+                      "h2d_bytes_per_step": int(pos.nbytes + mass.nbytes + h.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+                      "api": "Gravity(pos, mass, softening=h, kernel=Spline).tree_potentials(theta=0.7) (construct + walk)"}
+        if not args.no_cpu:
+            from oracle import oracle as O
+            ns = min(n, 1_000_000)  # bounded CPU sample: the reference's serial build is ~1 s per 1e6 particles
+            t0 = time.perf_counter()
+            ot = O.Tree(pos[:ns], mass[:ns], leaf, order, h[:ns], 1)
+            tb = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            ot.eval(theta, want=1)
+            tw = time.perf_counter() - t0
+            res["cpu_baseline"] = {"value": ns / (tb + tw), "unit": "particles/s", "cores": O.num_threads(), "kind": "port",
+                                   "sample": f"first {ns} particles of the same set: construct {tb:.2f} s (serial, as the "
+                                             f"reference) + potentials {tw:.2f} s (OpenMP)"}
+    del tree
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -306,13 +417,16 @@ def run_ours(args):
         r, cores, sample = cpu_reference_rate(pos, mass, 12.0)
         cpu = {"value": r / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
+    tree = None
+    if not args.no_tree:
+        tree = tree_section(args, rank, world, local, dev, barrier, meas_tf)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(n, world), "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
-            "tflops_20flop": FLOP_PER_INTERACTION * value * 1e9 / 1e12,
+            "tflops_20flop": FLOP_PER_INTERACTION * value * 1e9 / 1e12, "tree": tree,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -327,6 +441,8 @@ def main():
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-tree", action="store_true", help="skip the secondary tree-gravity section")
+    ap.add_argument("--tree-n", type=int, default=10_000_000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -41,10 +41,15 @@ def main():
         h = None
     kern = args.kernel if h is not None else None
     out = {"n": args.n, "set": args.set, "theta": args.theta, "order": args.order, "leaf": args.leaf}
-    r.Octree(pos[:1000], m[:1000], args.leaf, args.order)  # warm up context / pools
+    r.Octree(pos[:1000], m[:1000], args.leaf, args.order)  # warm up context
+    for _ in range(2):  # warm the stream-ordered memory pool, then free again
+        tree = r.Octree(pos, m, args.leaf, args.order, h, kern)
+        del tree
+    print("---- steady-state construct ----", file=sys.stderr)
     t0 = time.perf_counter()
     tree = r.Octree(pos, m, args.leaf, args.order, h, kern)
     out["construct_s"] = time.perf_counter() - t0
+    print("---- end construct ----", file=sys.stderr)
     out.update({k: v for k, v in tree.info().items() if k in ("n_nodes", "n_leaves", "depth")})
     for name, want in (("pot", 1), ("acc", 2)):
         ts = []
@@ -54,9 +59,6 @@ def main():
             ts.append(time.perf_counter() - t0)
         out[f"walk_{name}_s"] = min(ts)
         out[f"particles_per_s_{name}"] = args.n / min(ts)
-    t0 = time.perf_counter()
-    tree2 = r.Octree(pos, m, args.leaf, args.order, h, kern)
-    out["construct2_s"] = time.perf_counter() - t0
     if args.oracle:
         from oracle import oracle as O
         t0 = time.perf_counter()

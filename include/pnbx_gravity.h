@@ -154,6 +154,11 @@ int pnbx_tree_dump_payload(const pnbx_tree* t, double* mass, double* com, double
 /* Per-particle octant-path keys in original particle order (levels 1..21 in hi, 22..42 in lo). */
 int pnbx_tree_dump_keys(const pnbx_tree* t, uint64_t* key_hi, uint64_t* key_lo);
 
+/* Traversal statistics for the given targets (same target arguments as pnbx_tree_eval): totals of
+ * out4 = {node visits, accepted nodes, leaf visits, leaf particles} — the work model's inputs. */
+int pnbx_tree_walk_counters(pnbx_tree* t, const double* tgt_pos, int64_t m, int64_t tgt_begin, double theta,
+                            int64_t* out4, const pnbx_opts* opts);
+
 /* Stage timings of the last call on this thread (GRAVITY_TIMING analogue, tree.rs:5-21):
  * fills up to `cap` (label, milliseconds) pairs, returns the count. */
 int pnbx_last_timings(const char** labels, double* ms, int cap);

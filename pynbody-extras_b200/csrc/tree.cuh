@@ -76,6 +76,6 @@ struct pnbx_tree_impl {
 
 // tree_walk.cu
 void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int64_t m, int64_t tgt_begin,
-               double theta, int want, double* d_pot, double* d_acc, StageTimer& tm);
+               double theta, int want, double* d_pot, double* d_acc, StageTimer& tm, unsigned long long* d_counters);
 
 }  // namespace pnbx

@@ -28,7 +28,8 @@ template <class T>
 struct WalkArgs {
     const NodeGeom* geom;
     const NodeCtl* ctl;
-    const double* hmax;   // nullable
+    const double* gate2;  // per node (c * max(hmax,0))^2, nullable (no hmax payload)
+    unsigned long long* counters;  // counting pass only: visits, accepts, leaf visits, leaf particles
     const T* moments;     // (nn, K): float64 coefficients (T=double) or fp32 walk records (T=float)
     int K;
     const void* src;      // float4 (T=float) or double spos/smass (T=double)
@@ -85,7 +86,10 @@ __device__ __forceinline__ Vec4T<double> load_src<double>(const WalkArgs<double>
             a.smass ? a.smass[p] : 1.0};
 }
 
-template <int ORDER, int WANT, class T>
+// SMODE: 0 = no softening anywhere (no per-particle h, no hmax gate), 1 = Plummer, 2 = cubic spline,
+//        3 = decided at run time (float64 verification mode and the counting pass).
+// WANT == 0 is the counting pass: traversal decisions only, totals into a.counters.
+template <int ORDER, int WANT, class T, int SMODE>
 __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
     constexpr int DORD = (WANT & PNBX_WANT_ACC) ? (ORDER < 1 ? 1 : ORDER) : (ORDER < 2 ? 0 : ORDER);
     constexpr unsigned FULL = 0xffffffffu;
@@ -110,11 +114,20 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
         }
     }
     const T fx = (T)(tx - a.rc[0]), fy = (T)(ty - a.rc[1]), fz = (T)(tz - a.rc[2]);
-    const T th = (T)fmax(th64, 0.0);              // clamped target softening (tree.rs:115)
-    const bool soft = a.src_h != nullptr;         // softenings_opt.is_some() (tree.rs:116)
-    const bool spline = a.kernel == PNBX_KERNEL_SPLINE;
-    const double csep = spline ? 1.0 : 2.8;       // kernel.rs:20-28
+    const T th = (T)fmax(th64, 0.0);  // clamped target softening (tree.rs:115)
+    const bool soft = SMODE == 0 ? false : a.src_h != nullptr;  // softenings_opt.is_some() (tree.rs:116)
+    const bool spline = SMODE == 3 ? a.kernel == PNBX_KERNEL_SPLINE : SMODE == 2;
+    const bool gated = SMODE == 0 ? false : a.gate2 != nullptr;  // hmax payload present (tree.rs:57-59)
+    // softening gate threshold of this target: (c * max(h_t, 0))^2, c = 2.8 / 1.0 (kernel.rs:20-28). The node's
+    // own (c * max(hmax,0))^2 is precomputed; max() commutes with the monotone rounded ops, so
+    // max(gate_node, gate_t) == (c*h)*(c*h) for h = max(hmax, h_t) bit for bit (tree.rs:61-70).
+    double gate_t = 0.0;
+    if (gated && has_th) {
+        const double ch = __dmul_rn(spline ? 1.0 : 2.8, fmax(th64, 0.0));
+        gate_t = __dmul_rn(ch, ch);
+    }
     double P = 0.0, Ax = 0.0, Ay = 0.0, Az = 0.0;
+    long long n_visit = 0, n_accept = 0, n_leaf = 0, n_leafp = 0;
 
     bool active = valid;
     int resume = INT_MIN;
@@ -123,22 +136,28 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
         const NodeCtl c = a.ctl[idx];
         const NodeGeom gm = a.geom[idx];  // issued together with ctl: one memory round trip per visit
         if (!active && resume == idx) active = true;
+        if (WANT == 0 && active) ++n_visit;
         if (c.kind == -2) {  // zero mass: skip the subtree (tree.rs:1087-1090)
             idx = c.next_branch;
             continue;
         }
         if (c.kind >= 0) {  // leaf: always summed directly (tree.rs:1094-1112)
-            if (active) {
+            if (WANT == 0) {
+                if (active) { ++n_leaf; n_leafp += c.kind; }
+            } else if (active) {
                 T pot = T(0), ax = T(0), ay = T(0), az = T(0);
                 T lx = fx, ly = fy, lz = fz;
                 if (sizeof(T) == 4) {  // fp32 sources are stored relative to their leaf's COM
                     lx = (T)(tx - gm.com[0]); ly = (T)(ty - gm.com[1]); lz = (T)(tz - gm.com[2]);
                 }
                 for (int p = c.first; p < c.first + c.kind; ++p) {
-                    if (p == skip) continue;  // skip_self by index (tree.rs:130)
-                    const Vec4T<T> s = load_src<T>(a, p);
+                    Vec4T<T> s = load_src<T>(a, p);
                     const T dx = s.x - lx, dy = s.y - ly, dz = s.z - lz;
                     T r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                    if (p == skip) {  // skip_self by index (tree.rs:130): contributes exactly nothing
+                        s.w = T(0);
+                        r2 = T(1);
+                    }
                     T h = T(0);
                     if (soft) h = max(max(a.src_h[p], T(0)), th);  // tree.rs:234-235
                     T kpot, g;
@@ -175,24 +194,20 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
             dx = gm.com[0] - tx;
             dy = gm.com[1] - ty;
             dz = gm.com[2] - tz;
-            const double dist2 = fma(dx, dx, fma(dy, dy, __dmul_rn(dz, dz))) + DBL_MIN;
+            // (+ R2_TINY of tree.rs:1117 can only matter for dist2 < 1e-300, where nothing is accepted anyway)
+            const double dist2 = fma(dx, dx, fma(dy, dy, __dmul_rn(dz, dz)));
             bool soft_ok = true;
-            if (a.hmax) {  // node_soft_ok (tree.rs:55-71)
-                double h = fmax(a.hmax[idx], 0.0);
-                if (has_th) h = fmax(h, fmax(th64, 0.0));
-                if (h > 0.0) {
-                    const double ch = __dmul_rn(csep, h);
-                    soft_ok = dist2 > __dmul_rn(ch, ch);
-                }
-            }
+            if (gated) soft_ok = dist2 > fmax(a.gate2[idx], gate_t);  // node_soft_ok (tree.rs:55-71)
             accept = soft_ok && gm.size2 < __dmul_rn(a.theta2, dist2);
         }
         const unsigned need_open = __ballot_sync(FULL, active && !accept);
-        if (active && accept) {
+        if (WANT == 0) {
+            if (active && accept) ++n_accept;
+        } else if (active && accept) {
             if (sizeof(T) == 4 && ORDER <= 3) {
                 // fp32, order <= 3: contracted closed forms (multipole.cuh m2p_fast)
                 float pot = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-                mp::m2p_fast<ORDER, WANT>(reinterpret_cast<const float*>(a.moments) + (int64_t)idx * a.K, (float)dx, (float)dy,
+                mp::m2p_fast<ORDER, (WANT == 0 ? 1 : WANT)>(reinterpret_cast<const float*>(a.moments) + (int64_t)idx * a.K, (float)dx, (float)dy,
                                           (float)dz, pot, ax, ay, az);
                 if (WANT & PNBX_WANT_POT) P += (double)pot;
                 if (WANT & PNBX_WANT_ACC) { Ax += (double)ax; Ay += (double)ay; Az += (double)az; }
@@ -243,6 +258,21 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
             idx = c.next_branch;
         }
     }
+    if (WANT == 0) {  // warp-reduce, one atomic per warp per counter (integers: order-independent)
+        for (int o = 16; o > 0; o >>= 1) {
+            n_visit += __shfl_down_sync(FULL, n_visit, o);
+            n_accept += __shfl_down_sync(FULL, n_accept, o);
+            n_leaf += __shfl_down_sync(FULL, n_leaf, o);
+            n_leafp += __shfl_down_sync(FULL, n_leafp, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(a.counters + 0, (unsigned long long)n_visit);
+            atomicAdd(a.counters + 1, (unsigned long long)n_accept);
+            atomicAdd(a.counters + 2, (unsigned long long)n_leaf);
+            atomicAdd(a.counters + 3, (unsigned long long)n_leafp);
+        }
+        return;
+    }
     if (valid) {
         if (WANT & PNBX_WANT_POT) a.out_pot[oslot] = P;
         if (WANT & PNBX_WANT_ACC) {
@@ -251,13 +281,13 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
     }
 }
 
-template <class T>
+template <class T, int SMODE>
 void launch_walk(int order, int want, const WalkArgs<T>& a, cudaStream_t s) {
     const unsigned grid = (unsigned)ceil_div(a.m, WT);
-#define PNBX_W(O, W)                                                     \
-    if (order == O && want == W) {                                       \
-        PNBX_LAUNCH((walk_kernel<O, W, T>), grid, WT, 0, s, a);          \
-        return;                                                          \
+#define PNBX_W(O, W)                                                        \
+    if (order == O && want == W) {                                          \
+        PNBX_LAUNCH((walk_kernel<O, W, T, SMODE>), grid, WT, 0, s, a);      \
+        return;                                                             \
     }
     PNBX_W(1, 1) PNBX_W(1, 2) PNBX_W(1, 3)
     PNBX_W(2, 1) PNBX_W(2, 2) PNBX_W(2, 3)
@@ -266,6 +296,14 @@ void launch_walk(int order, int want, const WalkArgs<T>& a, cudaStream_t s) {
     PNBX_W(5, 1) PNBX_W(5, 2) PNBX_W(5, 3)
 #undef PNBX_W
     throw ArgError{PNBX_ERR_ARG, "internal: no walk kernel variant"};
+}
+
+// (c * max(hmax, 0))^2 per node for the current kernel
+__global__ void node_gates(const double* __restrict__ hmax, int64_t nn, double c, double* __restrict__ gate2) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nn) return;
+    const double ch = __dmul_rn(c, fmax(hmax[i], 0.0));
+    gate2[i] = __dmul_rn(ch, ch);
 }
 
 __global__ void point_keys(const double* __restrict__ pos, int64_t n, double cx, double cy, double cz, double hf0,
@@ -300,7 +338,7 @@ inline unsigned nb(int64_t n) { return (unsigned)std::max<int64_t>(1, ceil_div(n
 }  // namespace
 
 void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int64_t m, int64_t tgt_begin, double theta,
-               int want, double* d_pot, double* d_acc, StageTimer& tm) {
+               int want, double* d_pot, double* d_acc, StageTimer& tm, unsigned long long* d_counters) {
     cudaStream_t s = ex.stream;
     const bool self = d_tgt == nullptr;
     DevBuf<uint32_t> tlist, torder;
@@ -334,9 +372,15 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
     }
     tm.end();
 
+    DevBuf<double> gate2;
+    if (t.has_hmax) {
+        gate2.alloc((size_t)t.nn, s);
+        PNBX_LAUNCH(node_gates, nb(t.nn), 256, 0, s, t.hmax.p, t.nn, t.kernel == PNBX_KERNEL_SPLINE ? 1.0 : 2.8, gate2.p);
+    }
     auto fill = [&](auto& a) {
         a.geom = t.geom.p; a.ctl = t.ctl.p;
-        a.hmax = t.has_hmax ? t.hmax.p : nullptr;
+        a.gate2 = gate2.p;
+        a.counters = d_counters;
         a.spos = t.spos.p; a.smass = t.has_mass ? t.smass.p : nullptr;
         a.sh = t.has_h ? t.sh.p : nullptr;
         a.perm = t.perm.p;
@@ -350,16 +394,24 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
     const int order = std::max(1, t.order);  // order 0 and 1 are both monopoles
     tm.begin("octree.walk");
     kernel_events().begin(s);
-    if (ex.f64) {
+    if (d_counters) {  // counting pass (order-independent): traversal decisions only
         WalkArgs<double> a;
         fill(a);
         a.moments = t.moments.p; a.K = t.n_moments; a.src = nullptr; a.src_h = t.has_h ? t.sh.p : nullptr;
-        launch_walk<double>(order, want, a, s);
+        PNBX_LAUNCH((walk_kernel<1, 0, double, 3>), (unsigned)ceil_div(m, WT), WT, 0, s, a);
+    } else if (ex.f64) {
+        WalkArgs<double> a;
+        fill(a);
+        a.moments = t.moments.p; a.K = t.n_moments; a.src = nullptr; a.src_h = t.has_h ? t.sh.p : nullptr;
+        launch_walk<double, 3>(order, want, a, s);
     } else {
         WalkArgs<float> a;
         fill(a);
         a.moments = t.moments32.p; a.K = t.rec32; a.src = t.src32.p; a.src_h = t.has_h ? t.sh32.p : nullptr;
-        launch_walk<float>(order, want, a, s);
+        const bool any_soft = t.has_h || t.has_hmax;
+        if (!any_soft) launch_walk<float, 0>(order, want, a, s);
+        else if (t.kernel == PNBX_KERNEL_SPLINE) launch_walk<float, 2>(order, want, a, s);
+        else launch_walk<float, 1>(order, want, a, s);
     }
     kernel_events().end(s);
     PNBX_CUDA(cudaGetLastError());
@@ -394,9 +446,37 @@ extern "C" int pnbx_tree_eval(pnbx_tree* tp, const double* tgt_pos, int64_t m, i
         if (want & PNBX_WANT_ACC) o_acc.bind(out_acc, (size_t)3 * m, ex);
         InArray<double> i_tgt;
         if (!self) i_tgt.bind(tgt_pos, (size_t)3 * m, ex);
-        tree_walk(t, ex, self ? nullptr : i_tgt.d, m, tgt_begin, theta, want, o_pot.d, o_acc.d, tm);
+        tree_walk(t, ex, self ? nullptr : i_tgt.d, m, tgt_begin, theta, want, o_pot.d, o_acc.d, tm, nullptr);
         o_pot.finish(ex);
         o_acc.finish(ex);
+        finish_exec(ex);
+    });
+}
+
+// Traversal statistics of the walk tree.rs:1069-1370 would do for these targets: totals over all targets of
+// node visits, accepted nodes, leaf visits and leaf particles (the oracle's counters; input to the work model
+// of BASELINE.md §3). One extra decisions-only kernel; results are exact integers.
+extern "C" int pnbx_tree_walk_counters(pnbx_tree* tp, const double* tgt_pos, int64_t m, int64_t tgt_begin, double theta,
+                                       int64_t* out4, const pnbx_opts* opts) {
+    return guarded([&] {
+        if (!tp || !out4) throw ArgError{PNBX_ERR_ARG, "NULL argument"};
+        auto& t = *reinterpret_cast<pnbx_tree_impl*>(tp);
+        if (!t.has_payload) throw ArgError{PNBX_ERR_STATE, "mass payload not built; call build_mass() before compute"};
+        const bool self = tgt_pos == nullptr;
+        if (m < 0 || (self && (tgt_begin < 0 || tgt_begin + m > t.n))) throw ArgError{PNBX_ERR_ARG, "bad target range"};
+        pnbx_opts o = opts ? *opts : pnbx_opts{-1, PNBX_MEM_HOST, 0, 0, nullptr};
+        if (o.device < 0) o.device = t.device;
+        Exec ex = make_exec(&o);
+        StageTimer tm(ex.stream);
+        DevBuf<unsigned long long> cnt(4, ex.stream);
+        PNBX_CUDA(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(unsigned long long), ex.stream));
+        InArray<double> i_tgt;
+        if (!self) i_tgt.bind(tgt_pos, (size_t)3 * m, ex);
+        if (m > 0) tree_walk(t, ex, self ? nullptr : i_tgt.d, m, tgt_begin, theta, 1, nullptr, nullptr, tm, cnt.p);
+        unsigned long long h[4];
+        PNBX_CUDA(cudaMemcpyAsync(h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, ex.stream));
+        PNBX_CUDA(cudaStreamSynchronize(ex.stream));
+        for (int i = 0; i < 4; ++i) out4[i] = (int64_t)h[i];
         finish_exec(ex);
     });
 }

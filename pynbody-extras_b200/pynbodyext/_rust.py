@@ -100,6 +100,7 @@ def _load():
         L.pnbx_tree_dump_topology.argtypes = [_vp] + [_vp] * 10
         L.pnbx_tree_dump_payload.argtypes = [_vp] + [_vp] * 4
         L.pnbx_tree_dump_keys.argtypes = [_vp, _vp, _vp]
+        L.pnbx_tree_walk_counters.argtypes = [_vp, _vp, C.c_int64, C.c_int64, C.c_double, _vp, C.POINTER(pnbx_opts)]
     L.pnbx_last_timings.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.c_int]
     _lib = L
     return L
@@ -297,6 +298,16 @@ class Octree:
 
     def potentials_at_points(self, points, theta, threads=0):
         return self._eval(points, theta, WANT_POT, method="potentials_at_points")[0]
+
+    def walk_counters(self, theta, points=None, tgt_begin=0, count=None) -> dict:
+        """Totals over the targets of node visits / accepts / leaf visits / leaf particles of the walk
+        (decisions-only pass; equals the oracle's counters). Not in the reference."""
+        tgt = None if points is None else _vec3(points, "points")
+        m = (self._n if count is None else int(count)) if tgt is None else tgt.shape[0]
+        out = np.zeros(4, dtype=np.int64)
+        o = _opts(self._device, None)
+        _check(_load().pnbx_tree_walk_counters(self._h, _ptr(tgt), m, int(tgt_begin), float(theta), _ptr(out), C.byref(o)))
+        return dict(zip(("visits", "accepts", "leaf_visits", "leaf_particles"), out.tolist()))
 
     # -- introspection used by the parity tests (not in the reference)
     def info(self) -> dict:

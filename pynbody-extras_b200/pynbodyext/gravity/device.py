@@ -58,6 +58,59 @@ def direct_device(pos, mass=None, h=None, kernel=None, want=_b.WANT_ACC, targets
     return pot, acc
 
 
+class OctreeDevice:
+    """Octree built from device-resident float64 tensors (no host copies); evaluates into torch tensors on the
+    caller's current stream. Same semantics as ``pynbodyext._rust.Octree`` (reference gravity.rs:113-445)."""
+
+    def __init__(self, pos, mass=None, leaf_capacity=32, multipole_order=0, h=None, kernel=None, precision=None):
+        if kernel is None and h is not None:
+            raise ValueError("softenings require an explicit kernel; pass kernel=0/1 (or omit softenings)")
+        self._n = int(pos.shape[0])
+        self._dev = pos.device
+        self._precision = precision
+        self._h = C.c_void_p()
+        o = _dev_opts(pos, precision, False)
+        _b._check(_b._load().pnbx_tree_create(C.byref(self._h), _dptr(pos, 3), _dptr(mass), _dptr(h), self._n,
+                                              int(leaf_capacity), int(multipole_order), _b._kernel_code(kernel, 0),
+                                              C.byref(o)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and _b._lib is not None:
+            _b._lib.pnbx_tree_destroy(h)
+            self._h = C.c_void_p()
+
+    def info(self):
+        inf = _b.pnbx_tree_info()
+        _b._check(_b._load().pnbx_tree_get_info(self._h, C.byref(inf)))
+        return {f: getattr(inf, f) for f, _ in _b.pnbx_tree_info._fields_}
+
+    def eval(self, theta, want=_b.WANT_POT, targets=None, tgt_begin=0, count=None, kernel_events=False):
+        """(pot | None, acc | None) for own particles [tgt_begin, tgt_begin+count) or for `targets` (M,3)."""
+        torch = _torch()
+        if targets is None:
+            m = self._n - tgt_begin if count is None else int(count)
+            ref = torch.empty(0, device=self._dev, dtype=torch.float64)
+        else:
+            m = targets.shape[0]
+            ref = targets
+        pot = torch.empty(m, dtype=torch.float64, device=self._dev) if want & _b.WANT_POT else None
+        acc = torch.empty((m, 3), dtype=torch.float64, device=self._dev) if want & _b.WANT_ACC else None
+        o = _dev_opts(ref, self._precision, kernel_events)
+        _b._check(_b._load().pnbx_tree_eval(self._h, _dptr(targets, 3), m, int(tgt_begin), float(theta), want,
+                                            _dptr(pot), _dptr(acc), C.byref(o)))
+        return pot, acc
+
+    def walk_counters(self, theta, tgt_begin=0, count=None):
+        import numpy as np
+        m = self._n - tgt_begin if count is None else int(count)
+        out = np.zeros(4, dtype=np.int64)
+        o = _b._opts(self._dev.index, None)
+        _b._check(_b._load().pnbx_tree_walk_counters(self._h, None, m, int(tgt_begin), float(theta), out.ctypes.data,
+                                                     C.byref(o)))
+        return dict(zip(("visits", "accepts", "leaf_visits", "leaf_particles"), out.tolist()))
+
+
 def last_kernel_ms() -> float:
     ms = C.c_double(0.0)
     L = _b._load()

@@ -77,3 +77,36 @@ def direct_sharded(pos, mass, h, kernel, want, rank, world, device, targets=None
     pot_h = pot.cpu().numpy() if pot is not None else None
     acc_h = acc.cpu().numpy() if acc is not None else None
     return pot_h, acc_h, (tl, th)
+
+
+def tree_sharded(pos, mass, h, kernel, want, theta, rank, world, device, leaf_capacity=8, multipole_order=3,
+                 targets=None, group=None, precision=None):
+    """Sharded tree gravity: shard upload + one all-gather (as direct_sharded), then every rank builds the SAME
+    tree from the replicated sources (deterministic kernels => identical topology on every GPU; the build is
+    N-linear and ~10 ms per 1e7 particles) and walks only its own target shard. Returns (pot, acc, (lo, hi))."""
+    import torch
+
+    from . import device as gdev
+
+    n = pos.shape[0]
+    bounds = shard_bounds(n, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    per = max(bounds[r + 1] - bounds[r] for r in range(world))
+    dev = torch.device("cuda", device)
+    rows = torch.from_numpy(pack_shard(pos, mass, h, lo, hi, per)).to(dev, non_blocking=True)
+    allrows = replicate_sources(rows, bounds, group)
+    d_pos = allrows[:, 0:3].contiguous()
+    d_mass = allrows[:, 3].contiguous()
+    d_h = allrows[:, 4].contiguous() if h is not None else None
+    tree = gdev.OctreeDevice(d_pos, d_mass, leaf_capacity, multipole_order, d_h, kernel, precision=precision)
+    if targets is None:
+        pot, acc = tree.eval(theta, want, tgt_begin=lo, count=hi - lo)
+        tl, th = lo, hi
+    else:
+        tb = shard_bounds(targets.shape[0], world)
+        tl, th = tb[rank], tb[rank + 1]
+        d_t = torch.from_numpy(np.ascontiguousarray(targets[tl:th])).to(dev)
+        pot, acc = tree.eval(theta, want, targets=d_t)
+    pot_h = pot.cpu().numpy() if pot is not None else None
+    acc_h = acc.cpu().numpy() if acc is not None else None
+    return pot_h, acc_h, (tl, th)

@@ -264,3 +264,53 @@ def test_larger_tree_1e5_subsample_against_oracle():
     p, a = g._eval(None, 0.7, 3)
     assert rms_rel(p, p_o) < TOL32 and rms_rel_vec(a, a_o) < TOL32
     assert np.abs((p - p_o) / p_o).max() < 1e-4
+
+
+def test_walk_counters_equal_oracle_counters():
+    # lane-exact acceptance: the GPU walk visits / accepts / sums exactly what tree.rs:1069-1134 would
+    r = R()
+    pos, m = hernquist(20000, seed=81)
+    h = np.full(20000, 0.005)
+    g = r.Octree(pos, m, 8, 3, h, 1)
+    o = O.Tree(pos, m, 8, 3, h, 1)
+    for theta in (0.5, 0.7, 1.0):
+        _, _, c_o = o.eval(theta, want=1, counters=True)
+        assert g.walk_counters(theta) == c_o
+    q, _ = plummer(3000, seed=82, a=3.0)
+    _, _, c_o = o.eval(0.7, targets=q, want=1, counters=True)
+    assert g.walk_counters(0.7, points=q) == c_o
+
+
+def test_device_tree_api_matches_host_api():
+    import torch
+    from pynbodyext.gravity import device as gdev
+    pos, m = plummer(30000, seed=91)
+    h = np.full(30000, 0.01)
+    host = R().Octree(pos, m, 8, 3, h, 0)
+    d = torch.device("cuda", 0)
+    tree = gdev.OctreeDevice(torch.from_numpy(pos).to(d), torch.from_numpy(m).to(d), 8, 3, torch.from_numpy(h).to(d), 0)
+    assert tree.info()["n_nodes"] == host.info()["n_nodes"]
+    p_h, a_h = host._eval(None, 0.7, 3)
+    p_d, a_d = tree.eval(0.7, 3)
+    torch.cuda.synchronize()
+    assert np.array_equal(p_d.cpu().numpy(), p_h) and np.array_equal(a_d.cpu().numpy(), a_h)
+    p_s, _ = tree.eval(0.7, 1, tgt_begin=1000, count=5000)
+    assert np.array_equal(p_s.cpu().numpy(), p_h[1000:6000])
+    q = torch.from_numpy(pos[:777] * 1.5).to(d)
+    p_q, _ = tree.eval(0.7, 1, targets=q)
+    assert np.array_equal(p_q.cpu().numpy(), host.potentials_at_points(pos[:777] * 1.5, 0.7))
+
+
+def test_sharded_entry_points_single_rank():
+    # world = 1 path of the multi-GPU API (the all-gather is a no-op); multi-rank host logic is in test_sharded_gloo.py
+    from pynbodyext.gravity.sharded import direct_sharded, tree_sharded
+    pos, m = hernquist(20000, seed=92)
+    h = np.full(20000, 0.01)
+    p, a, (lo, hi) = direct_sharded(pos, m, h, kernel=0, want=3, rank=0, world=1, device=0)
+    assert (lo, hi) == (0, 20000)
+    p_o, a_o = O.direct(pos, m, h, kernel=0)
+    assert rms_rel(p, p_o) < TOL32 and rms_rel_vec(a, a_o) < TOL32
+    p, a, _ = tree_sharded(pos, m, h, kernel=0, want=3, theta=0.7, rank=0, world=1, device=0)
+    o = O.Tree(pos, m, 8, 3, h, 0)
+    p_o, a_o = o.eval(0.7)
+    assert rms_rel(p, p_o) < TOL32 and rms_rel_vec(a, a_o) < TOL32
