@@ -34,6 +34,15 @@ METRIC = "direct_sum_ginteractions_per_s"
 UNIT = "Ginteractions/s"
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def workload_config(n, n_gpus):
     return {
         "workload": f"Hernquist halo N={n} (a=1, r<=100a, seed 2), direct-sum accelerations, Plummer eps={EPS} "
@@ -266,7 +275,7 @@ def run_reference(args):
         "note": "CPU oracle (C++/OpenMP port of direct.rs; Rust toolchain absent); ms_per_step extrapolated "
                 "from the sampled rate to the full N(N-1) interactions",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -436,7 +445,7 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
             "tflops_20flop": FLOP_PER_INTERACTION * value * 1e9 / 1e12, "tree": tree,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -452,6 +461,12 @@ def main():
     ap.add_argument("--no-tree", action="store_true", help="skip the secondary tree-gravity section")
     ap.add_argument("--tree-n", type=int, default=10_000_000)
     args = ap.parse_args()
+    # Exactly one JSON line may reach stdout: route everything else written to fd 1 (NCCL's version banner,
+    # library chatter) to stderr and keep the real stdout for the result line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -84,7 +84,8 @@ def nfw_disc(n, seed=3, c=10.0, disc_frac_n=0.2, disc_frac_m=0.05, rd=0.03, zd_o
     soft = np.concatenate([np.full(nh, 1.0e-3), np.full(nd, 5.0e-4)])
     if dedup:
         pos = _dedup(pos, rng)
-    return np.ascontiguousarray(pos), mass, soft
+    order = rng.permutation(n)  # mixed particle order, so contiguous target shards cost about the same
+    return np.ascontiguousarray(pos[order]), np.ascontiguousarray(mass[order]), np.ascontiguousarray(soft[order])
 
 
 def zoom_families(n, seed=4, dedup=False):
@@ -117,7 +118,8 @@ def zoom_families(n, seed=4, dedup=False):
     soft = np.concatenate([np.full(ndm, 2.0e-3), h_gas, np.full(nstar, 5.0e-4)])
     if dedup:
         pos = _dedup(pos, rng)
-    return np.ascontiguousarray(pos), mass, soft
+    order = rng.permutation(n)
+    return np.ascontiguousarray(pos[order]), np.ascontiguousarray(mass[order]), np.ascontiguousarray(soft[order])
 
 
 def rz_grid_targets(m, seed=5, rmin=1e-3, rmax=5.0):
