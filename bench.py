@@ -169,20 +169,20 @@ def tree_section(args, rank, world, local, dev, barrier, peak_tf):
 
     for _ in range(2):  # warm the memory pool
         t = gdev.OctreeDevice(d_pos, d_mass, leaf, order, d_h, 1)
-        t.eval(theta, 1, tgt_begin=lo, count=hi - lo)
+        t.eval(theta, 1, tgt_begin=lo, count=hi - lo, tree_order=True)
         del t
     build_ms, tree = timed(lambda: gdev.OctreeDevice(d_pos, d_mass, leaf, order, d_h, 1), args.steps)
-    walk_pot_ms, _ = timed(lambda: tree.eval(theta, 1, tgt_begin=lo, count=hi - lo, kernel_events=True), args.steps)
+    walk_pot_ms, _ = timed(lambda: tree.eval(theta, 1, tgt_begin=lo, count=hi - lo, kernel_events=True, tree_order=True), args.steps)
     k_pot_ms = gdev.last_kernel_ms()
-    walk_acc_ms, _ = timed(lambda: tree.eval(theta, 2, tgt_begin=lo, count=hi - lo, kernel_events=True), args.steps)
+    walk_acc_ms, _ = timed(lambda: tree.eval(theta, 2, tgt_begin=lo, count=hi - lo, kernel_events=True, tree_order=True), args.steps)
     k_acc_ms = gdev.last_kernel_ms()
 
     def construct_and_pot():
         tt = gdev.OctreeDevice(d_pos, d_mass, leaf, order, d_h, 1)
-        return tt.eval(theta, 1, tgt_begin=lo, count=hi - lo)
+        return tt.eval(theta, 1, tgt_begin=lo, count=hi - lo, tree_order=True)
 
     both_ms, _ = timed(construct_and_pot, args.steps)
-    cnt = tree.walk_counters(theta, tgt_begin=lo, count=hi - lo)
+    cnt = tree.walk_counters(theta, tgt_begin=lo, count=hi - lo, tree_order=True)
     info = tree.info()
     m_t = hi - lo
     flop_acc = cnt["accepts"] * 140.0 + cnt["leaf_particles"] * 20.0 + cnt["visits"] * 10.0
@@ -455,7 +455,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--n", "--particles", dest="n", type=int, default=1_000_000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tree", action="store_true", help="skip the secondary tree-gravity section")

@@ -3,8 +3,8 @@ one box. One process per GPU (torchrun); every rank owns 1/world of the snapshot
 seed 4+rank — statistically the same set, no 1e8-particle host array per rank), uploads it, ONE all-gather
 replicates the sources, every rank builds the identical tree and walks its own target shard.
 
-  torchrun --nproc-per-node 8 benchmarks/tree_sharded_bench.py --n 100000000
-  python benchmarks/tree_sharded_bench.py --n 100000000          (single GPU)
+  torchrun --nproc-per-node 8 benchmarks/tree_sharded_bench.py --particles 100000000
+  python benchmarks/tree_sharded_bench.py --particles 100000000          (single GPU)
 
 Prints one JSON line with per-stage device times (max over ranks)."""
 import argparse
@@ -23,7 +23,7 @@ import numpy as np  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=100_000_000)
+    ap.add_argument("--particles", dest="n", type=int, default=100_000_000)
     ap.add_argument("--theta", type=float, default=0.7)
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--leaf", type=int, default=8)
@@ -73,6 +73,7 @@ def main():
 
     pot_h = torch.empty(hi - lo, dtype=torch.float64).pin_memory()   # caller-owned pinned result buffers
     acc_h = torch.empty((hi - lo, 3), dtype=torch.float64).pin_memory()
+    idx_h = torch.empty(hi - lo, dtype=torch.int64).pin_memory()      # original index of every result row
     best = None
     for rep in range(args.reps):
         t_h2d, rows = stage(lambda: rows_h.to(dev, non_blocking=True))
@@ -81,9 +82,10 @@ def main():
                                                        allrows[:, 4].contiguous()))
         del allrows, rows
         t_build, tree = stage(lambda: gdev.OctreeDevice(d_pos, d_mass, args.leaf, args.order, d_h, 1))
-        t_pot, pot = stage(lambda: tree.eval(args.theta, 1, tgt_begin=lo, count=hi - lo)[0])
-        t_acc, acc = stage(lambda: tree.eval(args.theta, 2, tgt_begin=lo, count=hi - lo)[1])
-        t_d2h, _ = stage(lambda: (pot_h.copy_(pot, non_blocking=True), acc_h.copy_(acc, non_blocking=True)))
+        t_pot, pot = stage(lambda: tree.eval(args.theta, 1, tgt_begin=lo, count=hi - lo, tree_order=True)[0])
+        t_acc, acc = stage(lambda: tree.eval(args.theta, 2, tgt_begin=lo, count=hi - lo, tree_order=True)[1])
+        t_d2h, _ = stage(lambda: (pot_h.copy_(pot, non_blocking=True), acc_h.copy_(acc, non_blocking=True),
+                                  idx_h.copy_(tree.order(lo, hi - lo), non_blocking=True)))
         res = {"h2d_ms": t_h2d, "allgather_ms": t_gather, "unpack_ms": t_split, "build_ms": t_build, "walk_pot_ms": t_pot,
                "walk_acc_ms": t_acc, "d2h_ms": t_d2h}
         res["total_pot_ms"] = t_h2d + t_gather + t_split + t_build + t_pot

@@ -60,6 +60,9 @@ extern "C" {
 
 /* pnbx_opts.flags */
 #define PNBX_FLAG_KERNEL_EVENTS 1 /* record CUDA events around the dominant kernel (pnbx_last_kernel_ms) */
+#define PNBX_FLAG_TREE_ORDER 2    /* pnbx_tree_eval self mode: tgt_begin/m select SORTED (tree-order) positions and
+                                     outputs are in that order; pnbx_tree_get_order gives the original indices.
+                                     Tree-order shards keep warps coherent: the multi-GPU sharding of choice. */
 
 typedef struct pnbx_opts {
     int32_t device;    /* CUDA ordinal; -1 = current device                       */
@@ -158,6 +161,9 @@ int pnbx_tree_dump_keys(const pnbx_tree* t, uint64_t* key_hi, uint64_t* key_lo);
  * out4 = {node visits, accepted nodes, leaf visits, leaf particles} — the work model's inputs. */
 int pnbx_tree_walk_counters(pnbx_tree* t, const double* tgt_pos, int64_t m, int64_t tgt_begin, double theta,
                             int64_t* out4, const pnbx_opts* opts);
+
+/* Original particle index of every tree-order position in [begin, begin+m) (host or device int64 per opts). */
+int pnbx_tree_get_order(const pnbx_tree* t, int64_t begin, int64_t m, int64_t* out, const pnbx_opts* opts);
 
 /* Stage timings of the last call on this thread (GRAVITY_TIMING analogue, tree.rs:5-21):
  * fills up to `cap` (label, milliseconds) pairs, returns the count. */

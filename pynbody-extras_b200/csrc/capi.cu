@@ -73,6 +73,7 @@ Exec make_exec(const pnbx_opts* opts) {
     ex.device_ptrs = opts && opts->mem_space == PNBX_MEM_DEVICE;
     ex.f64 = opts && opts->precision == PNBX_PREC_F64;
     ex.kernel_events = opts && (opts->flags & PNBX_FLAG_KERNEL_EVENTS);
+    ex.tree_order = opts && (opts->flags & PNBX_FLAG_TREE_ORDER);
     kernel_events().armed = ex.kernel_events;
     if (ex.kernel_events) kernel_events().valid = false;
     if (opts && (opts->stream || ex.device_ptrs)) {

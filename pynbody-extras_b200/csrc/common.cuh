@@ -70,6 +70,7 @@ struct Exec {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     bool kernel_events = false;
+    bool tree_order = false;
 };
 Exec make_exec(const pnbx_opts* opts);  // selects the device; throws if none
 void finish_exec(Exec& ex);             // sync (host mode) + release

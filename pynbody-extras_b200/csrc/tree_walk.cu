@@ -43,6 +43,7 @@ struct WalkArgs {
     int self;                 // 1: targets are tree particles
     const uint32_t* tlist;    // self: sorted positions to evaluate (nullable = identity)
     int64_t tgt_begin;        // self: output slot = perm[s] - tgt_begin
+    int tree_order;           // self: targets are sorted positions [tgt_begin, tgt_begin+m), output slot k
     const double* tgt;        // points: (m,3) float64
     const uint32_t* torder;   // points: walk order -> point index
     double theta2;
@@ -102,10 +103,10 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
     bool has_th = false;
     if (valid) {
         if (a.self) {
-            const uint32_t s = a.tlist ? a.tlist[k] : (uint32_t)k;
+            const uint32_t s = a.tree_order ? (uint32_t)(a.tgt_begin + k) : a.tlist ? a.tlist[k] : (uint32_t)k;
             tx = a.spos[3 * (int64_t)s]; ty = a.spos[3 * (int64_t)s + 1]; tz = a.spos[3 * (int64_t)s + 2];
             skip = (int)s;
-            oslot = (int64_t)a.perm[s] - a.tgt_begin;
+            oslot = a.tree_order ? k : (int64_t)a.perm[s] - a.tgt_begin;
             if (a.sh) { th64 = a.sh[s]; has_th = true; }  // target_h_opt = softenings[i] (tree.rs:1439)
         } else {
             const uint32_t q = a.torder[k];
@@ -343,8 +344,9 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
     const bool self = d_tgt == nullptr;
     DevBuf<uint32_t> tlist, torder;
     tm.begin("octree.walk.prepare_targets");
+    const bool tree_order = self && ex.tree_order;
     if (self) {
-        if (!(tgt_begin == 0 && m == t.n)) {  // shard: sorted positions whose particle lies in [tgt_begin, tgt_begin+m)
+        if (!tree_order && !(tgt_begin == 0 && m == t.n)) {  // shard: sorted positions whose particle lies in [tgt_begin, tgt_begin+m)
             DevBuf<uint8_t> flag((size_t)t.n, s);
             DevBuf<int32_t> nsel(1, s);
             tlist.alloc((size_t)t.n, s);
@@ -386,6 +388,7 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         a.perm = t.perm.p;
         a.m = m; a.self = self ? 1 : 0;
         a.tlist = tlist.p; a.tgt_begin = tgt_begin; a.tgt = d_tgt; a.torder = torder.p;
+        a.tree_order = tree_order ? 1 : 0;
         a.theta2 = theta * theta;
         a.rc[0] = t.root_center[0]; a.rc[1] = t.root_center[1]; a.rc[2] = t.root_center[2];
         a.kernel = t.kernel;
@@ -477,6 +480,33 @@ extern "C" int pnbx_tree_walk_counters(pnbx_tree* tp, const double* tgt_pos, int
         PNBX_CUDA(cudaMemcpyAsync(h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, ex.stream));
         PNBX_CUDA(cudaStreamSynchronize(ex.stream));
         for (int i = 0; i < 4; ++i) out4[i] = (int64_t)h[i];
+        finish_exec(ex);
+    });
+}
+
+// Original particle indices of sorted (tree-order) positions [begin, begin+m): the scatter map for results of
+// pnbx_tree_eval(..., PNBX_FLAG_TREE_ORDER). `out` is a host or device int64 array per opts->mem_space.
+namespace pnbx {
+__global__ void perm_to_i64(const uint32_t* __restrict__ perm, int64_t begin, int64_t m, int64_t* __restrict__ out) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m) out[k] = perm[begin + k];
+}
+}  // namespace pnbx
+extern "C" int pnbx_tree_get_order(const pnbx_tree* tp, int64_t begin, int64_t m, int64_t* out, const pnbx_opts* opts) {
+    return guarded([&] {
+        if (!tp || (!out && m > 0)) throw ArgError{PNBX_ERR_ARG, "NULL argument"};
+        const auto& t = *reinterpret_cast<const pnbx_tree_impl*>(tp);
+        if (begin < 0 || m < 0 || begin + m > t.n) throw ArgError{PNBX_ERR_ARG, "range outside [0, N)"};
+        pnbx_opts o = opts ? *opts : pnbx_opts{-1, PNBX_MEM_HOST, 0, 0, nullptr};
+        if (o.device < 0) o.device = t.device;
+        Exec ex = make_exec(&o);
+        if (m > 0) {
+            OutArray<int64_t> oa;
+            oa.bind(out, (size_t)m, ex);
+            PNBX_LAUNCH(perm_to_i64, (unsigned)ceil_div(m, 256), 256, 0, ex.stream, t.perm.p, begin, m, oa.d);
+            PNBX_CUDA(cudaGetLastError());
+            oa.finish(ex);
+        }
         finish_exec(ex);
     });
 }

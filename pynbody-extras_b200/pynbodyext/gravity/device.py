@@ -9,6 +9,7 @@ import ctypes as C
 import pynbodyext._rust as _b
 
 FLAG_KERNEL_EVENTS = 1
+FLAG_TREE_ORDER = 2
 
 
 def _torch():
@@ -85,8 +86,22 @@ class OctreeDevice:
         _b._check(_b._load().pnbx_tree_get_info(self._h, C.byref(inf)))
         return {f: getattr(inf, f) for f, _ in _b.pnbx_tree_info._fields_}
 
-    def eval(self, theta, want=_b.WANT_POT, targets=None, tgt_begin=0, count=None, kernel_events=False):
-        """(pot | None, acc | None) for own particles [tgt_begin, tgt_begin+count) or for `targets` (M,3)."""
+    def order(self, begin=0, count=None):
+        """Original particle index (int64 CUDA tensor) of tree-order positions [begin, begin+count)."""
+        torch = _torch()
+        m = self._n - begin if count is None else int(count)
+        out = torch.empty(m, dtype=torch.int64, device=self._dev)
+        o = _b._opts(self._dev.index, None, mem_space=_b.MEM_DEVICE, stream=torch.cuda.current_stream(self._dev).cuda_stream)
+        L = _b._load()
+        L.pnbx_tree_get_order.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(_b.pnbx_opts)]
+        _b._check(L.pnbx_tree_get_order(self._h, int(begin), m, out.data_ptr(), C.byref(o)))
+        return out
+
+    def eval(self, theta, want=_b.WANT_POT, targets=None, tgt_begin=0, count=None, kernel_events=False,
+             tree_order=False):
+        """(pot | None, acc | None) for own particles [tgt_begin, tgt_begin+count) or for `targets` (M,3).
+        tree_order=True: the range selects tree-order positions and results come back in that order
+        (use .order(tgt_begin, count) to scatter them) — coherent warps, the right sharding for multi-GPU."""
         torch = _torch()
         if targets is None:
             m = self._n - tgt_begin if count is None else int(count)
@@ -97,15 +112,19 @@ class OctreeDevice:
         pot = torch.empty(m, dtype=torch.float64, device=self._dev) if want & _b.WANT_POT else None
         acc = torch.empty((m, 3), dtype=torch.float64, device=self._dev) if want & _b.WANT_ACC else None
         o = _dev_opts(ref, self._precision, kernel_events)
+        if tree_order:
+            o.flags |= FLAG_TREE_ORDER
         _b._check(_b._load().pnbx_tree_eval(self._h, _dptr(targets, 3), m, int(tgt_begin), float(theta), want,
                                             _dptr(pot), _dptr(acc), C.byref(o)))
         return pot, acc
 
-    def walk_counters(self, theta, tgt_begin=0, count=None):
+    def walk_counters(self, theta, tgt_begin=0, count=None, tree_order=False):
         import numpy as np
         m = self._n - tgt_begin if count is None else int(count)
         out = np.zeros(4, dtype=np.int64)
         o = _b._opts(self._dev.index, None)
+        if tree_order:
+            o.flags |= FLAG_TREE_ORDER
         _b._check(_b._load().pnbx_tree_walk_counters(self._h, None, m, int(tgt_begin), float(theta), out.ctypes.data,
                                                      C.byref(o)))
         return dict(zip(("visits", "accepts", "leaf_visits", "leaf_particles"), out.tolist()))

@@ -83,7 +83,11 @@ def tree_sharded(pos, mass, h, kernel, want, theta, rank, world, device, leaf_ca
                  targets=None, group=None, precision=None):
     """Sharded tree gravity: shard upload + one all-gather (as direct_sharded), then every rank builds the SAME
     tree from the replicated sources (deterministic kernels => identical topology on every GPU; the build is
-    N-linear and ~10 ms per 1e7 particles) and walks only its own target shard. Returns (pot, acc, (lo, hi))."""
+    N-linear and ~10 ms per 1e7 particles) and walks only its own target shard.
+
+    Self mode shards are contiguous in TREE order (coherent warps, similar cost per rank), so a rank's results
+    belong to scattered particles: returns (pot, acc, idx) with idx the original particle indices (int64) of this
+    rank's results. At-points mode returns (pot, acc, (lo, hi)) for the contiguous target slice."""
     import torch
 
     from . import device as gdev
@@ -100,8 +104,9 @@ def tree_sharded(pos, mass, h, kernel, want, theta, rank, world, device, leaf_ca
     d_h = allrows[:, 4].contiguous() if h is not None else None
     tree = gdev.OctreeDevice(d_pos, d_mass, leaf_capacity, multipole_order, d_h, kernel, precision=precision)
     if targets is None:
-        pot, acc = tree.eval(theta, want, tgt_begin=lo, count=hi - lo)
-        tl, th = lo, hi
+        pot, acc = tree.eval(theta, want, tgt_begin=lo, count=hi - lo, tree_order=True)
+        idx = tree.order(lo, hi - lo).cpu().numpy()
+        return (pot.cpu().numpy() if pot is not None else None, acc.cpu().numpy() if acc is not None else None, idx)
     else:
         tb = shard_bounds(targets.shape[0], world)
         tl, th = tb[rank], tb[rank + 1]

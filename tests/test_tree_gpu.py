@@ -296,6 +296,11 @@ def test_device_tree_api_matches_host_api():
     assert np.array_equal(p_d.cpu().numpy(), p_h) and np.array_equal(a_d.cpu().numpy(), a_h)
     p_s, _ = tree.eval(0.7, 1, tgt_begin=1000, count=5000)
     assert np.array_equal(p_s.cpu().numpy(), p_h[1000:6000])
+    # tree-order shards: same numbers, delivered in tree order with the scatter map
+    p_t, a_t = tree.eval(0.7, 3, tgt_begin=7000, count=9000, tree_order=True)
+    idx = tree.order(7000, 9000).cpu().numpy()
+    assert np.array_equal(p_t.cpu().numpy(), p_h[idx]) and np.array_equal(a_t.cpu().numpy(), a_h[idx])
+    assert np.array_equal(np.sort(tree.order().cpu().numpy()), np.arange(30000))
     q = torch.from_numpy(pos[:777] * 1.5).to(d)
     p_q, _ = tree.eval(0.7, 1, targets=q)
     assert np.array_equal(p_q.cpu().numpy(), host.potentials_at_points(pos[:777] * 1.5, 0.7))
@@ -310,7 +315,8 @@ def test_sharded_entry_points_single_rank():
     assert (lo, hi) == (0, 20000)
     p_o, a_o = O.direct(pos, m, h, kernel=0)
     assert rms_rel(p, p_o) < TOL32 and rms_rel_vec(a, a_o) < TOL32
-    p, a, _ = tree_sharded(pos, m, h, kernel=0, want=3, theta=0.7, rank=0, world=1, device=0)
+    p, a, idx = tree_sharded(pos, m, h, kernel=0, want=3, theta=0.7, rank=0, world=1, device=0)
     o = O.Tree(pos, m, 8, 3, h, 0)
     p_o, a_o = o.eval(0.7)
-    assert rms_rel(p, p_o) < TOL32 and rms_rel_vec(a, a_o) < TOL32
+    assert np.array_equal(np.sort(idx), np.arange(20000))
+    assert rms_rel(p, p_o[idx]) < TOL32 and rms_rel_vec(a, a_o[idx]) < TOL32
