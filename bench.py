@@ -169,22 +169,22 @@ def tree_section(args, rank, world, local, dev, barrier, peak_tf):
 
     for _ in range(2):  # warm the memory pool
         t = gdev.OctreeDevice(d_pos, d_mass, leaf, order, d_h, 1)
-        t.eval(theta, 1, tgt_begin=lo, count=hi - lo, tree_order=True)
+        t.eval(theta, 1, shard=(rank, world))
         del t
     build_ms, tree = timed(lambda: gdev.OctreeDevice(d_pos, d_mass, leaf, order, d_h, 1), args.steps)
-    walk_pot_ms, _ = timed(lambda: tree.eval(theta, 1, tgt_begin=lo, count=hi - lo, kernel_events=True, tree_order=True), args.steps)
+    walk_pot_ms, _ = timed(lambda: tree.eval(theta, 1, shard=(rank, world), kernel_events=True), args.steps)
     k_pot_ms = gdev.last_kernel_ms()
-    walk_acc_ms, _ = timed(lambda: tree.eval(theta, 2, tgt_begin=lo, count=hi - lo, kernel_events=True, tree_order=True), args.steps)
+    walk_acc_ms, _ = timed(lambda: tree.eval(theta, 2, shard=(rank, world), kernel_events=True), args.steps)
     k_acc_ms = gdev.last_kernel_ms()
 
     def construct_and_pot():
         tt = gdev.OctreeDevice(d_pos, d_mass, leaf, order, d_h, 1)
-        return tt.eval(theta, 1, tgt_begin=lo, count=hi - lo, tree_order=True)
+        return tt.eval(theta, 1, shard=(rank, world))
 
     both_ms, _ = timed(construct_and_pot, args.steps)
-    cnt = tree.walk_counters(theta, tgt_begin=lo, count=hi - lo, tree_order=True)
+    cnt = tree.walk_counters(theta, shard=(rank, world))
     info = tree.info()
-    m_t = hi - lo
+    m_t = gdev.shard_count(n, world, rank)
     flop_acc = cnt["accepts"] * 140.0 + cnt["leaf_particles"] * 20.0 + cnt["visits"] * 10.0
     flop_pot = cnt["accepts"] * 120.0 + cnt["leaf_particles"] * 20.0 + cnt["visits"] * 10.0
     res = {

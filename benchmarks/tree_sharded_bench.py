@@ -71,9 +71,11 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), r
 
-    pot_h = torch.empty(hi - lo, dtype=torch.float64).pin_memory()   # caller-owned pinned result buffers
-    acc_h = torch.empty((hi - lo, 3), dtype=torch.float64).pin_memory()
-    idx_h = torch.empty(hi - lo, dtype=torch.int64).pin_memory()      # original index of every result row
+    m_r = gdev.shard_count(n, world, rank)                            # block-cyclic tree-order shard of this rank
+    cap = per + gdev.SHARD_BLOCK
+    pot_h = torch.empty(cap, dtype=torch.float64).pin_memory()        # caller-owned pinned result buffers
+    acc_h = torch.empty((cap, 3), dtype=torch.float64).pin_memory()
+    idx_h = torch.empty(cap, dtype=torch.int64).pin_memory()          # original index of every result row
     best = None
     for rep in range(args.reps):
         t_h2d, rows = stage(lambda: rows_h.to(dev, non_blocking=True))
@@ -82,10 +84,10 @@ def main():
                                                        allrows[:, 4].contiguous()))
         del allrows, rows
         t_build, tree = stage(lambda: gdev.OctreeDevice(d_pos, d_mass, args.leaf, args.order, d_h, 1))
-        t_pot, pot = stage(lambda: tree.eval(args.theta, 1, tgt_begin=lo, count=hi - lo, tree_order=True)[0])
-        t_acc, acc = stage(lambda: tree.eval(args.theta, 2, tgt_begin=lo, count=hi - lo, tree_order=True)[1])
-        t_d2h, _ = stage(lambda: (pot_h.copy_(pot, non_blocking=True), acc_h.copy_(acc, non_blocking=True),
-                                  idx_h.copy_(tree.order(lo, hi - lo), non_blocking=True)))
+        t_pot, pot = stage(lambda: tree.eval(args.theta, 1, shard=(rank, world))[0])
+        t_acc, acc = stage(lambda: tree.eval(args.theta, 2, shard=(rank, world))[1])
+        t_d2h, _ = stage(lambda: (pot_h[:m_r].copy_(pot, non_blocking=True), acc_h[:m_r].copy_(acc, non_blocking=True),
+                                  idx_h[:m_r].copy_(tree.order(shard=(rank, world)), non_blocking=True)))
         res = {"h2d_ms": t_h2d, "allgather_ms": t_gather, "unpack_ms": t_split, "build_ms": t_build, "walk_pot_ms": t_pot,
                "walk_acc_ms": t_acc, "d2h_ms": t_d2h}
         res["total_pot_ms"] = t_h2d + t_gather + t_split + t_build + t_pot

@@ -63,6 +63,9 @@ extern "C" {
 #define PNBX_FLAG_TREE_ORDER 2    /* pnbx_tree_eval self mode: tgt_begin/m select SORTED (tree-order) positions and
                                      outputs are in that order; pnbx_tree_get_order gives the original indices.
                                      Tree-order shards keep warps coherent: the multi-GPU sharding of choice. */
+#define PNBX_FLAG_BLOCK_CYCLIC 4  /* with PNBX_FLAG_TREE_ORDER: block-cyclic instead of contiguous shards (every rank
+                                     samples every region of the tree => equal cost per rank); tgt_begin is ignored,
+                                     m must be pnbx_shard_count(n, block, world, rank). */
 
 typedef struct pnbx_opts {
     int32_t device;    /* CUDA ordinal; -1 = current device                       */
@@ -71,6 +74,11 @@ typedef struct pnbx_opts {
     int32_t flags;     /* bit mask of PNBX_FLAG_*                                 */
     void* stream;      /* cudaStream_t to order work on. NULL = a library-owned stream for
                           PNBX_MEM_HOST, the CUDA default stream for PNBX_MEM_DEVICE */
+    /* PNBX_FLAG_BLOCK_CYCLIC only: this rank's targets are the tree-order blocks b with b % shard_world ==
+     * shard_rank, block = shard_block consecutive tree-order positions (0 = 4096). */
+    int32_t shard_rank;
+    int32_t shard_world;
+    int64_t shard_block;
 } pnbx_opts;
 
 typedef struct pnbx_tree pnbx_tree; /* opaque; owns device copies of the sources */
@@ -162,8 +170,12 @@ int pnbx_tree_dump_keys(const pnbx_tree* t, uint64_t* key_hi, uint64_t* key_lo);
 int pnbx_tree_walk_counters(pnbx_tree* t, const double* tgt_pos, int64_t m, int64_t tgt_begin, double theta,
                             int64_t* out4, const pnbx_opts* opts);
 
+/* Number of tree-order positions owned by `rank` under block-cyclic sharding of n positions. */
+int64_t pnbx_shard_count(int64_t n, int64_t block, int32_t world, int32_t rank);
+
 /* Original particle index of every tree-order position in [begin, begin+m) (host or device int64 per opts). */
 int pnbx_tree_get_order(const pnbx_tree* t, int64_t begin, int64_t m, int64_t* out, const pnbx_opts* opts);
+/* (with PNBX_FLAG_BLOCK_CYCLIC in opts->flags: the positions of that rank's block-cyclic shard, `begin` ignored) */
 
 /* Stage timings of the last call on this thread (GRAVITY_TIMING analogue, tree.rs:5-21):
  * fills up to `cap` (label, milliseconds) pairs, returns the count. */

@@ -74,6 +74,14 @@ Exec make_exec(const pnbx_opts* opts) {
     ex.f64 = opts && opts->precision == PNBX_PREC_F64;
     ex.kernel_events = opts && (opts->flags & PNBX_FLAG_KERNEL_EVENTS);
     ex.tree_order = opts && (opts->flags & PNBX_FLAG_TREE_ORDER);
+    ex.block_cyclic = ex.tree_order && (opts->flags & PNBX_FLAG_BLOCK_CYCLIC);
+    if (ex.block_cyclic) {
+        ex.shard_world = opts->shard_world;
+        ex.shard_rank = opts->shard_rank;
+        ex.shard_block = opts->shard_block > 0 ? opts->shard_block : 4096;
+        if (ex.shard_world < 1 || ex.shard_rank < 0 || ex.shard_rank >= ex.shard_world)
+            throw ArgError{PNBX_ERR_ARG, "bad shard_rank / shard_world"};
+    }
     kernel_events().armed = ex.kernel_events;
     if (ex.kernel_events) kernel_events().valid = false;
     if (opts && (opts->stream || ex.device_ptrs)) {
@@ -241,6 +249,14 @@ int pnbx_device_count(void) {
         return 0;
     }
     return n;
+}
+int64_t pnbx_shard_count(int64_t n, int64_t block, int32_t world, int32_t rank) {
+    if (block <= 0) block = 4096;
+    if (n <= 0 || world < 1 || rank < 0 || rank >= world) return 0;
+    const int64_t full = n / block, tail = n % block;
+    int64_t cnt = (full / world + (rank < full % world ? 1 : 0)) * block;
+    if (tail && full % world == rank) cnt += tail;
+    return cnt;
 }
 int pnbx_last_kernel_ms(double* ms) {
     auto& k = pnbx::kernel_events();

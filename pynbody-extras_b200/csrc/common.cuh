@@ -71,6 +71,9 @@ struct Exec {
     bool own_stream = false;
     bool kernel_events = false;
     bool tree_order = false;
+    bool block_cyclic = false;
+    int shard_rank = 0, shard_world = 1;
+    int64_t shard_block = 4096;
 };
 Exec make_exec(const pnbx_opts* opts);  // selects the device; throws if none
 void finish_exec(Exec& ex);             // sync (host mode) + release

@@ -44,6 +44,8 @@ struct WalkArgs {
     const uint32_t* tlist;    // self: sorted positions to evaluate (nullable = identity)
     int64_t tgt_begin;        // self: output slot = perm[s] - tgt_begin
     int tree_order;           // self: targets are sorted positions [tgt_begin, tgt_begin+m), output slot k
+    int64_t cyc_block;        // > 0: block-cyclic tree-order shard: position of target k =
+    int cyc_rank, cyc_world;  //      ((k / B) * world + rank) * B + k % B
     const double* tgt;        // points: (m,3) float64
     const uint32_t* torder;   // points: walk order -> point index
     double theta2;
@@ -103,7 +105,9 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
     bool has_th = false;
     if (valid) {
         if (a.self) {
-            const uint32_t s = a.tree_order ? (uint32_t)(a.tgt_begin + k) : a.tlist ? a.tlist[k] : (uint32_t)k;
+            uint32_t s;
+            if (a.cyc_block > 0) s = (uint32_t)(((k / a.cyc_block) * a.cyc_world + a.cyc_rank) * a.cyc_block + k % a.cyc_block);
+            else s = a.tree_order ? (uint32_t)(a.tgt_begin + k) : a.tlist ? a.tlist[k] : (uint32_t)k;
             tx = a.spos[3 * (int64_t)s]; ty = a.spos[3 * (int64_t)s + 1]; tz = a.spos[3 * (int64_t)s + 2];
             skip = (int)s;
             oslot = a.tree_order ? k : (int64_t)a.perm[s] - a.tgt_begin;
@@ -389,6 +393,8 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         a.m = m; a.self = self ? 1 : 0;
         a.tlist = tlist.p; a.tgt_begin = tgt_begin; a.tgt = d_tgt; a.torder = torder.p;
         a.tree_order = tree_order ? 1 : 0;
+        a.cyc_block = (tree_order && ex.block_cyclic) ? ex.shard_block : 0;
+        a.cyc_rank = ex.shard_rank; a.cyc_world = ex.shard_world;
         a.theta2 = theta * theta;
         a.rc[0] = t.root_center[0]; a.rc[1] = t.root_center[1]; a.rc[2] = t.root_center[2];
         a.kernel = t.kernel;
@@ -436,7 +442,13 @@ extern "C" int pnbx_tree_eval(pnbx_tree* tp, const double* tgt_pos, int64_t m, i
         if ((want & PNBX_WANT_POT) && !out_pot && m > 0) throw ArgError{PNBX_ERR_ARG, "out_pot is NULL"};
         if ((want & PNBX_WANT_ACC) && !out_acc && m > 0) throw ArgError{PNBX_ERR_ARG, "out_acc is NULL"};
         const bool self = tgt_pos == nullptr;
-        if (self && (tgt_begin < 0 || tgt_begin + m > t.n)) throw ArgError{PNBX_ERR_ARG, "target shard outside [0, N)"};
+        const bool cyc = self && opts && (opts->flags & PNBX_FLAG_TREE_ORDER) && (opts->flags & PNBX_FLAG_BLOCK_CYCLIC);
+        if (cyc) {
+            if (m != pnbx_shard_count(t.n, opts->shard_block, opts->shard_world, opts->shard_rank))
+                throw ArgError{PNBX_ERR_ARG, "m must equal pnbx_shard_count(n, block, world, rank) for a block-cyclic shard"};
+        } else if (self && (tgt_begin < 0 || tgt_begin + m > t.n)) {
+            throw ArgError{PNBX_ERR_ARG, "target shard outside [0, N)"};
+        }
         if (m >= ((int64_t)1 << 31) - 16) throw ArgError{PNBX_ERR_ARG, "M must be < 2^31"};
         pnbx_opts o = opts ? *opts : pnbx_opts{-1, PNBX_MEM_HOST, 0, 0, nullptr};
         if (o.device < 0) o.device = t.device;
@@ -466,7 +478,8 @@ extern "C" int pnbx_tree_walk_counters(pnbx_tree* tp, const double* tgt_pos, int
         auto& t = *reinterpret_cast<pnbx_tree_impl*>(tp);
         if (!t.has_payload) throw ArgError{PNBX_ERR_STATE, "mass payload not built; call build_mass() before compute"};
         const bool self = tgt_pos == nullptr;
-        if (m < 0 || (self && (tgt_begin < 0 || tgt_begin + m > t.n))) throw ArgError{PNBX_ERR_ARG, "bad target range"};
+        const bool cyc = self && opts && (opts->flags & PNBX_FLAG_TREE_ORDER) && (opts->flags & PNBX_FLAG_BLOCK_CYCLIC);
+        if (m < 0 || (self && !cyc && (tgt_begin < 0 || tgt_begin + m > t.n))) throw ArgError{PNBX_ERR_ARG, "bad target range"};
         pnbx_opts o = opts ? *opts : pnbx_opts{-1, PNBX_MEM_HOST, 0, 0, nullptr};
         if (o.device < 0) o.device = t.device;
         Exec ex = make_exec(&o);
@@ -487,23 +500,33 @@ extern "C" int pnbx_tree_walk_counters(pnbx_tree* tp, const double* tgt_pos, int
 // Original particle indices of sorted (tree-order) positions [begin, begin+m): the scatter map for results of
 // pnbx_tree_eval(..., PNBX_FLAG_TREE_ORDER). `out` is a host or device int64 array per opts->mem_space.
 namespace pnbx {
-__global__ void perm_to_i64(const uint32_t* __restrict__ perm, int64_t begin, int64_t m, int64_t* __restrict__ out) {
+__global__ void perm_to_i64(const uint32_t* __restrict__ perm, int64_t begin, int64_t m, int64_t cyc_block, int cyc_rank,
+                            int cyc_world, int64_t* __restrict__ out) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < m) out[k] = perm[begin + k];
+    if (k >= m) return;
+    const int64_t s = cyc_block > 0 ? ((k / cyc_block) * cyc_world + cyc_rank) * cyc_block + k % cyc_block : begin + k;
+    out[k] = perm[s];
 }
 }  // namespace pnbx
 extern "C" int pnbx_tree_get_order(const pnbx_tree* tp, int64_t begin, int64_t m, int64_t* out, const pnbx_opts* opts) {
     return guarded([&] {
         if (!tp || (!out && m > 0)) throw ArgError{PNBX_ERR_ARG, "NULL argument"};
         const auto& t = *reinterpret_cast<const pnbx_tree_impl*>(tp);
-        if (begin < 0 || m < 0 || begin + m > t.n) throw ArgError{PNBX_ERR_ARG, "range outside [0, N)"};
         pnbx_opts o = opts ? *opts : pnbx_opts{-1, PNBX_MEM_HOST, 0, 0, nullptr};
         if (o.device < 0) o.device = t.device;
+        o.flags |= (o.flags & PNBX_FLAG_BLOCK_CYCLIC) ? PNBX_FLAG_TREE_ORDER : 0;
         Exec ex = make_exec(&o);
+        if (ex.block_cyclic) {
+            if (m != pnbx_shard_count(t.n, ex.shard_block, ex.shard_world, ex.shard_rank))
+                throw ArgError{PNBX_ERR_ARG, "m must equal pnbx_shard_count(n, block, world, rank)"};
+        } else if (begin < 0 || m < 0 || begin + m > t.n) {
+            throw ArgError{PNBX_ERR_ARG, "range outside [0, N)"};
+        }
         if (m > 0) {
             OutArray<int64_t> oa;
             oa.bind(out, (size_t)m, ex);
-            PNBX_LAUNCH(perm_to_i64, (unsigned)ceil_div(m, 256), 256, 0, ex.stream, t.perm.p, begin, m, oa.d);
+            PNBX_LAUNCH(perm_to_i64, (unsigned)ceil_div(m, 256), 256, 0, ex.stream, t.perm.p, begin, m,
+                        ex.block_cyclic ? ex.shard_block : (int64_t)0, ex.shard_rank, ex.shard_world, oa.d);
             PNBX_CUDA(cudaGetLastError());
             oa.finish(ex);
         }

@@ -47,6 +47,9 @@ class pnbx_opts(C.Structure):
         ("precision", C.c_int32),
         ("flags", C.c_int32),
         ("stream", C.c_void_p),
+        ("shard_rank", C.c_int32),
+        ("shard_world", C.c_int32),
+        ("shard_block", C.c_int64),
     ]
 
 
@@ -141,6 +144,7 @@ def _opts(device=None, precision=None, mem_space=MEM_HOST, stream=None):
         raise ValueError("precision must be 'f32' or 'f64'")
     o.flags = 0
     o.stream = stream
+    o.shard_rank, o.shard_world, o.shard_block = 0, 1, 0
     return o
 
 

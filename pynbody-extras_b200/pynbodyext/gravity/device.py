@@ -10,6 +10,16 @@ import pynbodyext._rust as _b
 
 FLAG_KERNEL_EVENTS = 1
 FLAG_TREE_ORDER = 2
+FLAG_BLOCK_CYCLIC = 4
+SHARD_BLOCK = 4096
+
+
+def shard_count(n, world, rank, block=SHARD_BLOCK) -> int:
+    """Targets owned by `rank` under block-cyclic tree-order sharding (pnbx_shard_count)."""
+    L = _b._load()
+    L.pnbx_shard_count.restype = C.c_int64
+    L.pnbx_shard_count.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32]
+    return int(L.pnbx_shard_count(int(n), int(block), int(world), int(rank)))
 
 
 def _torch():
@@ -86,25 +96,37 @@ class OctreeDevice:
         _b._check(_b._load().pnbx_tree_get_info(self._h, C.byref(inf)))
         return {f: getattr(inf, f) for f, _ in _b.pnbx_tree_info._fields_}
 
-    def order(self, begin=0, count=None):
-        """Original particle index (int64 CUDA tensor) of tree-order positions [begin, begin+count)."""
+    def _shard(self, o, shard):
+        if shard is not None:
+            rank, world = shard
+            o.flags |= FLAG_TREE_ORDER | FLAG_BLOCK_CYCLIC
+            o.shard_rank, o.shard_world, o.shard_block = int(rank), int(world), SHARD_BLOCK
+            return shard_count(self._n, world, rank)
+        return None
+
+    def order(self, begin=0, count=None, shard=None):
+        """Original particle index (int64 CUDA tensor) of tree-order positions [begin, begin+count), or of the
+        block-cyclic shard ``shard=(rank, world)``."""
         torch = _torch()
-        m = self._n - begin if count is None else int(count)
-        out = torch.empty(m, dtype=torch.int64, device=self._dev)
         o = _b._opts(self._dev.index, None, mem_space=_b.MEM_DEVICE, stream=torch.cuda.current_stream(self._dev).cuda_stream)
+        ms = self._shard(o, shard)
+        m = ms if ms is not None else (self._n - begin if count is None else int(count))
+        out = torch.empty(m, dtype=torch.int64, device=self._dev)
         L = _b._load()
         L.pnbx_tree_get_order.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(_b.pnbx_opts)]
         _b._check(L.pnbx_tree_get_order(self._h, int(begin), m, out.data_ptr(), C.byref(o)))
         return out
 
     def eval(self, theta, want=_b.WANT_POT, targets=None, tgt_begin=0, count=None, kernel_events=False,
-             tree_order=False):
+             tree_order=False, shard=None):
         """(pot | None, acc | None) for own particles [tgt_begin, tgt_begin+count) or for `targets` (M,3).
         tree_order=True: the range selects tree-order positions and results come back in that order
-        (use .order(tgt_begin, count) to scatter them) — coherent warps, the right sharding for multi-GPU."""
+        (use .order(tgt_begin, count) to scatter them) — coherent warps, the right sharding for multi-GPU.
+        shard=(rank, world): block-cyclic tree-order shard of that rank (equal cost per rank); .order(shard=...)."""
         torch = _torch()
         if targets is None:
-            m = self._n - tgt_begin if count is None else int(count)
+            m = shard_count(self._n, shard[1], shard[0]) if shard is not None else (
+                self._n - tgt_begin if count is None else int(count))
             ref = torch.empty(0, device=self._dev, dtype=torch.float64)
         else:
             m = targets.shape[0]
@@ -114,17 +136,19 @@ class OctreeDevice:
         o = _dev_opts(ref, self._precision, kernel_events)
         if tree_order:
             o.flags |= FLAG_TREE_ORDER
+        self._shard(o, shard)
         _b._check(_b._load().pnbx_tree_eval(self._h, _dptr(targets, 3), m, int(tgt_begin), float(theta), want,
                                             _dptr(pot), _dptr(acc), C.byref(o)))
         return pot, acc
 
-    def walk_counters(self, theta, tgt_begin=0, count=None, tree_order=False):
+    def walk_counters(self, theta, tgt_begin=0, count=None, tree_order=False, shard=None):
         import numpy as np
-        m = self._n - tgt_begin if count is None else int(count)
         out = np.zeros(4, dtype=np.int64)
         o = _b._opts(self._dev.index, None)
         if tree_order:
             o.flags |= FLAG_TREE_ORDER
+        ms = self._shard(o, shard)
+        m = ms if ms is not None else (self._n - tgt_begin if count is None else int(count))
         _b._check(_b._load().pnbx_tree_walk_counters(self._h, None, m, int(tgt_begin), float(theta), out.ctypes.data,
                                                      C.byref(o)))
         return dict(zip(("visits", "accepts", "leaf_visits", "leaf_particles"), out.tolist()))

@@ -85,7 +85,8 @@ def tree_sharded(pos, mass, h, kernel, want, theta, rank, world, device, leaf_ca
     tree from the replicated sources (deterministic kernels => identical topology on every GPU; the build is
     N-linear and ~10 ms per 1e7 particles) and walks only its own target shard.
 
-    Self mode shards are contiguous in TREE order (coherent warps, similar cost per rank), so a rank's results
+    Self mode shards are block-cyclic in TREE order (blocks of 4096 consecutive tree-order particles dealt round-robin:
+    coherent warps, and every rank samples every region of the tree, so ranks cost the same), so a rank's results
     belong to scattered particles: returns (pot, acc, idx) with idx the original particle indices (int64) of this
     rank's results. At-points mode returns (pot, acc, (lo, hi)) for the contiguous target slice."""
     import torch
@@ -104,8 +105,8 @@ def tree_sharded(pos, mass, h, kernel, want, theta, rank, world, device, leaf_ca
     d_h = allrows[:, 4].contiguous() if h is not None else None
     tree = gdev.OctreeDevice(d_pos, d_mass, leaf_capacity, multipole_order, d_h, kernel, precision=precision)
     if targets is None:
-        pot, acc = tree.eval(theta, want, tgt_begin=lo, count=hi - lo, tree_order=True)
-        idx = tree.order(lo, hi - lo).cpu().numpy()
+        pot, acc = tree.eval(theta, want, shard=(rank, world))
+        idx = tree.order(shard=(rank, world)).cpu().numpy()
         return (pot.cpu().numpy() if pot is not None else None, acc.cpu().numpy() if acc is not None else None, idx)
     else:
         tb = shard_bounds(targets.shape[0], world)

@@ -301,6 +301,15 @@ def test_device_tree_api_matches_host_api():
     idx = tree.order(7000, 9000).cpu().numpy()
     assert np.array_equal(p_t.cpu().numpy(), p_h[idx]) and np.array_equal(a_t.cpu().numpy(), a_h[idx])
     assert np.array_equal(np.sort(tree.order().cpu().numpy()), np.arange(30000))
+    # block-cyclic shards of 3 ranks: disjoint, complete, identical numbers
+    seen = []
+    for rk in range(3):
+        p_s, a_s = tree.eval(0.7, 3, shard=(rk, 3))
+        ix = tree.order(shard=(rk, 3)).cpu().numpy()
+        assert len(ix) == gdev.shard_count(30000, 3, rk)
+        assert np.array_equal(p_s.cpu().numpy(), p_h[ix]) and np.array_equal(a_s.cpu().numpy(), a_h[ix])
+        seen.append(ix)
+    assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(30000))
     q = torch.from_numpy(pos[:777] * 1.5).to(d)
     p_q, _ = tree.eval(0.7, 1, targets=q)
     assert np.array_equal(p_q.cpu().numpy(), host.potentials_at_points(pos[:777] * 1.5, 0.7))
