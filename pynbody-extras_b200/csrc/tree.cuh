@@ -12,18 +12,18 @@ namespace pnbx {
 constexpr int KEY_LEVELS_HI = 21;  // 3 bits per level in a 64-bit word (63 bits used)
 constexpr int KEY_LEVELS = 42;     // hi + lo words
 
-// 32-byte record fetched on every node visit (one broadcast load per warp).
-struct alignas(32) NodeGeom {
+// One 64-byte, 64-byte-aligned record per node: everything a visit needs in two 32-byte sectors of one line,
+// fetched with a single broadcast load per warp.
+struct alignas(64) NodeRec {
     double com[3];
-    double size2;  // (2*half)^2, tree.rs:794-798
-};
-// 16-byte control record.
-struct alignas(16) NodeCtl {
+    double size2;         // (2*half)^2, tree.rs:794-798
+    double gate2;         // (c * max(hmax,0))^2 for the tree's current kernel (tree.rs:61-70), 0 without hmax
     int32_t next_branch;  // tree.rs:736-776; -1 = end of walk
     int32_t first;        // internal: first_subnode; leaf: first particle (sorted order)
     int32_t kind;         // >= 0: leaf with `kind` particles; -1: internal; -2: zero mass (skip subtree)
     int32_t pad;
 };
+static_assert(sizeof(NodeRec) == 64, "NodeRec must be one 64-byte record");
 
 struct pnbx_tree_impl {
     int device = 0;
@@ -70,8 +70,7 @@ struct pnbx_tree_impl {
     DevBuf<double> moments;            // (nn, n_moments) float64
     DevBuf<float> moments32;           // fp32 walk records, rec32 floats per node (multipole.cuh: m2p_fast layout for
     int rec32 = 0;                     // order <= 3, the plain coefficients padded to a multiple of 4 for orders 4, 5)
-    DevBuf<NodeGeom> geom;
-    DevBuf<NodeCtl> ctl;
+    DevBuf<NodeRec> rec;               // walk records (reference numbering)
 };
 
 // tree_walk.cu

@@ -379,24 +379,33 @@ __global__ void __launch_bounds__(128) payload_level(PayloadArgs a) {
 }
 
 __global__ void build_walk_records(const double* __restrict__ nmass, const double* __restrict__ ncom,
-                                   const double* __restrict__ half, const uint8_t* __restrict__ nchild,
-                                   const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
-                                   const int32_t* __restrict__ first_subnode, const int32_t* __restrict__ next_branch,
-                                   int64_t nn, NodeGeom* __restrict__ geom, NodeCtl* __restrict__ ctl) {
+                                   const double* __restrict__ half, const double* __restrict__ hmax, double csep,
+                                   const uint8_t* __restrict__ nchild, const uint32_t* __restrict__ start,
+                                   const uint32_t* __restrict__ count, const int32_t* __restrict__ first_subnode,
+                                   const int32_t* __restrict__ next_branch, int64_t nn, NodeRec* __restrict__ rec) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nn) return;
-    NodeGeom g;
-    g.com[0] = ncom[3 * i]; g.com[1] = ncom[3 * i + 1]; g.com[2] = ncom[3 * i + 2];
+    NodeRec r;
+    r.com[0] = ncom[3 * i]; r.com[1] = ncom[3 * i + 1]; r.com[2] = ncom[3 * i + 2];
     const double s = half[i] * 2.0;
-    g.size2 = __dmul_rn(s, s);
-    geom[i] = g;
-    NodeCtl c;
-    c.next_branch = next_branch[i];
-    if (nmass[i] == 0.0) { c.kind = -2; c.first = -1; }          // tree.rs:1087-1090
-    else if (nchild[i] == 0) { c.kind = (int32_t)count[i]; c.first = (int32_t)start[i]; }
-    else { c.kind = -1; c.first = first_subnode[i]; }
-    c.pad = 0;
-    ctl[i] = c;
+    r.size2 = __dmul_rn(s, s);
+    r.gate2 = 0.0;
+    if (hmax) {
+        const double ch = __dmul_rn(csep, fmax(hmax[i], 0.0));
+        r.gate2 = __dmul_rn(ch, ch);
+    }
+    r.next_branch = next_branch[i];
+    if (nmass[i] == 0.0) { r.kind = -2; r.first = -1; }          // tree.rs:1087-1090
+    else if (nchild[i] == 0) { r.kind = (int32_t)count[i]; r.first = (int32_t)start[i]; }
+    else { r.kind = -1; r.first = first_subnode[i]; }
+    r.pad = 0;
+    rec[i] = r;
+}
+__global__ void update_gates(const double* __restrict__ hmax, double csep, int64_t nn, NodeRec* __restrict__ rec) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nn) return;
+    const double ch = __dmul_rn(csep, fmax(hmax[i], 0.0));
+    rec[i].gate2 = __dmul_rn(ch, ch);
 }
 // fp32 walk records from the float64 moments (layout: multipole.cuh, m2p_fast)
 __global__ void pack_walk_moments(const double* __restrict__ mom, int64_t nn, int order, int K, int rec,
@@ -626,10 +635,10 @@ void build_mass_payload(pnbx_tree_impl& t, cudaStream_t s, StageTimer& tm) {
             default: PNBX_LAUNCH(payload_level<5>, nblk(a.count, 128), 128, 0, s, a); break;
         }
     }
-    t.geom.alloc((size_t)nn, s);
-    t.ctl.alloc((size_t)nn, s);
-    PNBX_LAUNCH(build_walk_records, nblk(nn), 256, 0, s, t.nmass.p, t.ncom.p, t.half.p, t.node_nchild.p, t.node_start.p,
-                t.node_count.p, t.first_subnode.p, t.next_branch.p, nn, t.geom.p, t.ctl.p);
+    t.rec.alloc((size_t)nn, s);
+    PNBX_LAUNCH(build_walk_records, nblk(nn), 256, 0, s, t.nmass.p, t.ncom.p, t.half.p, t.has_hmax ? t.hmax.p : nullptr,
+                t.kernel == PNBX_KERNEL_SPLINE ? 1.0 : 2.8, t.node_nchild.p, t.node_start.p, t.node_count.p,
+                t.first_subnode.p, t.next_branch.p, nn, t.rec.p);
     if (t.n > 0) {
         if (!t.src32.p) t.src32.alloc((size_t)t.n, s);
         PNBX_LAUNCH(leaf_local_sources, nblk(nn), 256, 0, s, t.node_nchild.p, t.node_start.p, t.node_count.p, t.ncom.p,
@@ -788,7 +797,15 @@ extern "C" int pnbx_tree_set_kernel(pnbx_tree* tp, int kernel) {
         if (!tp) throw ArgError{PNBX_ERR_ARG, "tree is NULL"};
         if (kernel != PNBX_KERNEL_PLUMMER && kernel != PNBX_KERNEL_SPLINE)
             throw ArgError{PNBX_ERR_ARG, "kernel must be 0 (Plummer) or 1 (CubicSplineW2)"};
-        reinterpret_cast<pnbx_tree_impl*>(tp)->kernel = kernel;
+        auto& t = *reinterpret_cast<pnbx_tree_impl*>(tp);
+        if (t.kernel != kernel && t.has_payload && t.has_hmax) {  // the gate factor c depends on the kernel (kernel.rs:20-28)
+            Exec ex = tree_exec(t);
+            PNBX_LAUNCH(update_gates, nblk(t.nn), 256, 0, ex.stream, t.hmax.p, kernel == PNBX_KERNEL_SPLINE ? 1.0 : 2.8, t.nn,
+                        t.rec.p);
+            PNBX_CUDA(cudaGetLastError());
+            finish_exec(ex);
+        }
+        t.kernel = kernel;
     });
 }
 

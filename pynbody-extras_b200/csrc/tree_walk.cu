@@ -26,9 +26,8 @@ struct Vec4T {
 
 template <class T>
 struct WalkArgs {
-    const NodeGeom* geom;
-    const NodeCtl* ctl;
-    const double* gate2;  // per node (c * max(hmax,0))^2, nullable (no hmax payload)
+    const NodeRec* rec;
+    int gated;            // hmax payload present (tree.rs:57-59)
     unsigned long long* counters;  // counting pass only: visits, accepts, leaf visits, leaf particles
     const T* moments;     // (nn, K): float64 coefficients (T=double) or fp32 walk records (T=float)
     int K;
@@ -120,9 +119,9 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
     }
     const T fx = (T)(tx - a.rc[0]), fy = (T)(ty - a.rc[1]), fz = (T)(tz - a.rc[2]);
     const T th = (T)fmax(th64, 0.0);  // clamped target softening (tree.rs:115)
-    const bool soft = SMODE == 0 ? false : a.src_h != nullptr;  // softenings_opt.is_some() (tree.rs:116)
+    const bool soft = SMODE == 0 ? false : SMODE == 3 ? a.src_h != nullptr : true;  // softenings_opt.is_some() (tree.rs:116)
     const bool spline = SMODE == 3 ? a.kernel == PNBX_KERNEL_SPLINE : SMODE == 2;
-    const bool gated = SMODE == 0 ? false : a.gate2 != nullptr;  // hmax payload present (tree.rs:57-59)
+    const bool gated = SMODE == 0 ? false : a.gated != 0;
     // softening gate threshold of this target: (c * max(h_t, 0))^2, c = 2.8 / 1.0 (kernel.rs:20-28). The node's
     // own (c * max(hmax,0))^2 is precomputed; max() commutes with the monotone rounded ops, so
     // max(gate_node, gate_t) == (c*h)*(c*h) for h = max(hmax, h_t) bit for bit (tree.rs:61-70).
@@ -138,8 +137,8 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
     int resume = INT_MIN;
     int idx = __ballot_sync(FULL, valid) ? 0 : -1;
     while (idx >= 0) {
-        const NodeCtl c = a.ctl[idx];
-        const NodeGeom gm = a.geom[idx];  // issued together with ctl: one memory round trip per visit
+        const NodeRec c = a.rec[idx];  // one 64-byte record: one memory round trip per visit
+        const NodeRec& gm = c;
         if (!active && resume == idx) active = true;
         if (WANT == 0 && active) ++n_visit;
         if (c.kind == -2) {  // zero mass: skip the subtree (tree.rs:1087-1090)
@@ -202,7 +201,7 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
             // (+ R2_TINY of tree.rs:1117 can only matter for dist2 < 1e-300, where nothing is accepted anyway)
             const double dist2 = fma(dx, dx, fma(dy, dy, __dmul_rn(dz, dz)));
             bool soft_ok = true;
-            if (gated) soft_ok = dist2 > fmax(a.gate2[idx], gate_t);  // node_soft_ok (tree.rs:55-71)
+            if (gated) soft_ok = dist2 > fmax(c.gate2, gate_t);  // node_soft_ok (tree.rs:55-71)
             accept = soft_ok && gm.size2 < __dmul_rn(a.theta2, dist2);
         }
         const unsigned need_open = __ballot_sync(FULL, active && !accept);
@@ -303,14 +302,6 @@ void launch_walk(int order, int want, const WalkArgs<T>& a, cudaStream_t s) {
     throw ArgError{PNBX_ERR_ARG, "internal: no walk kernel variant"};
 }
 
-// (c * max(hmax, 0))^2 per node for the current kernel
-__global__ void node_gates(const double* __restrict__ hmax, int64_t nn, double c, double* __restrict__ gate2) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nn) return;
-    const double ch = __dmul_rn(c, fmax(hmax[i], 0.0));
-    gate2[i] = __dmul_rn(ch, ch);
-}
-
 __global__ void point_keys(const double* __restrict__ pos, int64_t n, double cx, double cy, double cz, double hf0,
                            uint64_t* __restrict__ key) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,14 +369,16 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
     }
     tm.end();
 
-    DevBuf<double> gate2;
-    if (t.has_hmax) {
-        gate2.alloc((size_t)t.nn, s);
-        PNBX_LAUNCH(node_gates, nb(t.nn), 256, 0, s, t.hmax.p, t.nn, t.kernel == PNBX_KERNEL_SPLINE ? 1.0 : 2.8, gate2.p);
+    // SMODE 1/2 kernels read the softening array unconditionally: give them zeros if the tree has an hmax payload
+    // but no softenings any more (set_softenings(None) after the build)
+    DevBuf<float> zero_h;
+    if (!t.has_h && t.has_hmax && !ex.f64 && !d_counters) {
+        zero_h.alloc((size_t)t.n + 4, s);
+        PNBX_CUDA(cudaMemsetAsync(zero_h.p, 0, ((size_t)t.n + 4) * sizeof(float), s));
     }
     auto fill = [&](auto& a) {
-        a.geom = t.geom.p; a.ctl = t.ctl.p;
-        a.gate2 = gate2.p;
+        a.rec = t.rec.p;
+        a.gated = t.has_hmax ? 1 : 0;
         a.counters = d_counters;
         a.spos = t.spos.p; a.smass = t.has_mass ? t.smass.p : nullptr;
         a.sh = t.has_h ? t.sh.p : nullptr;
@@ -416,7 +409,7 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
     } else {
         WalkArgs<float> a;
         fill(a);
-        a.moments = t.moments32.p; a.K = t.rec32; a.src = t.src32.p; a.src_h = t.has_h ? t.sh32.p : nullptr;
+        a.moments = t.moments32.p; a.K = t.rec32; a.src = t.src32.p; a.src_h = t.has_h ? t.sh32.p : zero_h.p;
         const bool any_soft = t.has_h || t.has_hmax;
         if (!any_soft) launch_walk<float, 0>(order, want, a, s);
         else if (t.kernel == PNBX_KERNEL_SPLINE) launch_walk<float, 2>(order, want, a, s);
