@@ -114,6 +114,10 @@ def cpu_reference_rate(pos, mass, target_seconds=12.0):
     from oracle import oracle as O
     n = pos.shape[0]
     h = np.full(n, EPS)
+    try:  # torchrun exports OMP_NUM_THREADS=1; the reference (rayon, threads=0) uses every core it may run on
+        O.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     cores = O.num_threads()
     probe = max(cores * 32, 1024)
     O.direct(pos[:4096], mass[:4096], h[:4096], targets=pos[:512], kernel=0, want=2)  # spin up the OpenMP team

@@ -18,8 +18,21 @@
 namespace pnbx {
 namespace {
 
-constexpr int DT = 256;     // threads per block
-constexpr int TPT = 4;      // targets per thread
+#ifndef PNBX_DT
+#define PNBX_DT 256
+#endif
+#ifndef PNBX_TPT
+#define PNBX_TPT 4
+#endif
+#ifndef PNBX_MINB
+#define PNBX_MINB 2
+#endif
+#ifndef PNBX_UNROLL
+#define PNBX_UNROLL 4
+#endif
+constexpr int DT = PNBX_DT;    // threads per block
+constexpr int TPT = PNBX_TPT;  // targets per thread
+constexpr int UNROLL_F2 = PNBX_UNROLL;  // pair records per unrolled step of the packed loop
 constexpr int STAGES = 3;   // smem pipeline depth
 constexpr int TILE32 = 512; // sources per stage, fp32 path (8 KB of float4)
 constexpr int TILE64 = 256; // sources per stage, fp64 verification path (8 KB of double4)
@@ -153,7 +166,7 @@ __device__ __forceinline__ void interact(T xi, T yi, T zi, T e, const Vec4<T>& s
 }
 
 template <int WANT, int SOFT, class T, int TILE>
-__global__ void __launch_bounds__(DT, 2)
+__global__ void __launch_bounds__(DT, PNBX_MINB)
 direct_kernel(const Vec4<T>* __restrict__ src, const T* __restrict__ src_h, int64_t n_src,
               const Vec4<T>* __restrict__ tgt, const T* __restrict__ tgt_h, int64_t m, int64_t self_base,
               T eps2_const, int tiles_per_split, double* __restrict__ out_pot, double* __restrict__ out_acc) {
@@ -299,7 +312,7 @@ __device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
 constexpr int TILEP = TILE32 / 2;  // pair records per stage
 
 template <int WANT, bool ALLFMA>
-__global__ void __launch_bounds__(DT, 2)
+__global__ void __launch_bounds__(DT, PNBX_MINB)
 direct_kernel_f2(const Pair8* __restrict__ src, int64_t n_src, const Vec4<float>* __restrict__ tgt, int64_t m,
                  int64_t self_base, float eps2_const, int tiles_per_split, double* __restrict__ out_pot,
                  double* __restrict__ out_acc) {
@@ -368,7 +381,7 @@ direct_kernel_f2(const Pair8* __restrict__ src, int64_t n_src, const Vec4<float>
             f2_t ax[TPT], ay[TPT], az[TPT], p[TPT];
 #pragma unroll
             for (int k = 0; k < TPT; ++k) ax[k] = ay[k] = az[k] = p[k] = 0ull;  // {+0.f, +0.f}
-#pragma unroll 4
+#pragma unroll UNROLL_F2
             for (int q = 0; q < TILEP; ++q) {
                 const ulonglong4 v = *reinterpret_cast<const ulonglong4*>(&s_src[st][q]);  // {x0x1, y0y1, z0z1, m0m1}
 #pragma unroll

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
             // (+ R2_TINY of tree.rs:1117 can only matter for dist2 < 1e-300, where nothing is accepted anyway)
             const double dist2 = fma(dx, dx, fma(dy, dy, __dmul_rn(dz, dz)));
             bool soft_ok = true;
-            if (gated) soft_ok = dist2 > fmax(c.gate2, gate_t);  // node_soft_ok (tree.rs:55-71)
+            if (gated) soft_ok = dist2 > c.gate2 && dist2 > gate_t;  // dist2 > max(gates): node_soft_ok (tree.rs:55-71)
             accept = soft_ok && gm.size2 < __dmul_rn(a.theta2, dist2);
         }
         const unsigned need_open = __ballot_sync(FULL, active && !accept);

@@ -75,3 +75,20 @@ def test_python_api_surface():
     sig = inspect.signature(r.Octree.__init__)
     assert [sig.parameters[p].default for p in ("masses", "leaf_capacity", "multipole_order", "softenings", "kernel")] == [None, 32, 0, None, None]
     assert calculate_acceleration is not None
+
+
+def test_compute_fails_loudly_without_a_gpu():
+    # no CPU fallback: on a machine without a CUDA device every compute entry point must raise, not return numbers
+    import numpy as np
+    import pynbodyext._rust as r
+
+    if r._load().pnbx_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    pos = np.random.default_rng(0).random((16, 3))
+    with pytest.raises(RuntimeError, match="no CUDA device available"):
+        r.direct_potentials_py(pos)
+    with pytest.raises(RuntimeError, match="no CUDA device available"):
+        r.Octree(pos, np.ones(16))
+    from pynbodyext.gravity import Gravity
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Gravity(pos, np.ones(16)).tree_potentials()
