@@ -16,4 +16,6 @@ class SimArray(np.ndarray):
 
     def in_units(self, new):
         new = _u.parse(new)
-        return SimArray(np.asarray(self) * self.units.ratio(new), new)
+        out = SimArray(np.asarray(self) * self.units.ratio(new), new)
+        out.sim = self.sim  # pynbody keeps the snapshot reference through unit conversions
+        return out
