@@ -329,3 +329,44 @@ def test_sharded_entry_points_single_rank():
     p_o, a_o = o.eval(0.7)
     assert np.array_equal(np.sort(idx), np.arange(20000))
     assert rms_rel(p, p_o[idx]) < TOL32 and rms_rel_vec(a, a_o[idx]) < TOL32
+
+
+def test_zero_mass_particles_and_nodes():
+    # zero-mass nodes are skipped as a whole (tree.rs:1087-1090), zero-mass children are left out of COM / M2M
+    # (tree.rs:913, 1051); a clump of massless tracers forms zero-mass leaves and subtrees
+    r = R()
+    pos, m = plummer(4000, seed=101)
+    tracers = np.random.default_rng(102).normal(0.0, 0.01, (600, 3)) + np.array([3.0, 3.0, 3.0])
+    pos = np.concatenate([pos, tracers])
+    m = np.concatenate([m, np.zeros(600)])
+    m[::7] = 0.0
+    g = r.Octree(pos, m, 8, 3)
+    o = O.Tree(pos, m, 8, 3)
+    assert_same_topology(g, o)
+    assert_same_payload(g, o)
+    assert (o.payload()["mass"] == 0.0).sum() > 10
+    p_o, a_o = o.eval(0.7)
+    p, a = g._eval(None, 0.7, 3, precision="f64")
+    assert rms_rel(p, p_o) < TOL64 and rms_rel_vec(a, a_o) < TOL64
+    p, a = g._eval(None, 0.7, 3)
+    assert rms_rel(p, p_o) < TOL32 and rms_rel_vec(a, a_o) < TOL32
+    assert g.walk_counters(0.7) == o.eval(0.7, want=1, counters=True)[2]
+
+
+def test_negative_and_zero_softenings_follow_reference_clamps():
+    # tree leaf sums clamp every h at 0 (tree.rs:37,115,234); direct self mode does not
+    r = R()
+    pos, m = plummer(2000, seed=103)
+    h = np.random.default_rng(104).uniform(-0.02, 0.05, 2000)
+    h[:100] = 0.0
+    for kernel in (0, 1):
+        g = r.Octree(pos, m, 8, 3, h, kernel)
+        o = O.Tree(pos, m, 8, 3, h, kernel)
+        assert_same_payload(g, o)
+        p_o, a_o = o.eval(0.7)
+        p, a = g._eval(None, 0.7, 3, precision="f64")
+        assert rms_rel(p, p_o) < TOL64 and rms_rel_vec(a, a_o) < TOL64
+        p_d, a_d = O.direct(pos, m, h, kernel=kernel)
+        p = r.direct_potentials_py(pos, m, 0, h, kernel, precision="f64")
+        a = r.direct_accelerations_py(pos, m, 0, h, kernel, precision="f64")
+        assert rms_rel(p, p_d) < TOL64 and rms_rel_vec(a, a_d) < TOL64
