@@ -200,7 +200,9 @@ def tree_section(args, rank, world, local, dev, barrier, peak_tf):
         "construct_plus_pot_ms": both_ms,
         "walk_only_particles_per_s": {"pot": n / (walk_pot_ms * 1e-3), "acc": n / (walk_acc_ms * 1e-3)},
         "nodes": info["n_nodes"], "depth": info["depth"],
-        "per_target": {k: v / m_t for k, v in cnt.items()},
+        "per_target": {k: v / m_t for k, v in cnt.items() if k != "warp_visits"},
+        "warp_union_visits_per_warp": cnt["warp_visits"] / max(1, (m_t + 31) // 32),
+        "lane_visit_efficiency": cnt["visits"] / max(1, 32 * cnt["warp_visits"]),
         "roofline_walk": {
             "bound": "fp32", "kernel": "walk_kernel<3,acc,f32>", "unit": "TFLOP/s",
             "achieved": flop_acc / (k_acc_ms * 1e-3) / 1e12, "peak": peak_tf,

@@ -166,9 +166,11 @@ int pnbx_tree_dump_payload(const pnbx_tree* t, double* mass, double* com, double
 int pnbx_tree_dump_keys(const pnbx_tree* t, uint64_t* key_hi, uint64_t* key_lo);
 
 /* Traversal statistics for the given targets (same target arguments as pnbx_tree_eval): totals of
- * out4 = {node visits, accepted nodes, leaf visits, leaf particles} — the work model's inputs. */
+ * out5 = {node visits, accepted nodes, leaf visits, leaf particles} summed over targets — the work model's
+ * inputs, equal to the reference walk's own counts — and out5[4] = nodes visited per warp summed over warps
+ * (the union of 32 targets' paths, i.e. what the warp-cooperative walk really traverses). */
 int pnbx_tree_walk_counters(pnbx_tree* t, const double* tgt_pos, int64_t m, int64_t tgt_begin, double theta,
-                            int64_t* out4, const pnbx_opts* opts);
+                            int64_t* out5, const pnbx_opts* opts);
 
 /* Number of tree-order positions owned by `rank` under block-cyclic sharding of n positions. */
 int64_t pnbx_shard_count(int64_t n, int64_t block, int32_t world, int32_t rank);

@@ -28,7 +28,7 @@ template <class T>
 struct WalkArgs {
     const NodeRec* rec;
     int gated;            // hmax payload present (tree.rs:57-59)
-    unsigned long long* counters;  // counting pass only: visits, accepts, leaf visits, leaf particles
+    unsigned long long* counters;  // counting pass only: visits, accepts, leaf visits, leaf particles, warp visits
     const T* moments;     // (nn, K): float64 coefficients (T=double) or fp32 walk records (T=float)
     int K;
     const void* src;      // float4 (T=float) or double spos/smass (T=double)
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
         gate_t = __dmul_rn(ch, ch);
     }
     double P = 0.0, Ax = 0.0, Ay = 0.0, Az = 0.0;
-    long long n_visit = 0, n_accept = 0, n_leaf = 0, n_leafp = 0;
+    long long n_visit = 0, n_accept = 0, n_leaf = 0, n_leafp = 0, n_wvisit = 0;
 
     bool active = valid;
     int resume = INT_MIN;
@@ -140,7 +140,10 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
         const NodeRec c = a.rec[idx];  // one 64-byte record: one memory round trip per visit
         const NodeRec& gm = c;
         if (!active && resume == idx) active = true;
-        if (WANT == 0 && active) ++n_visit;
+        if (WANT == 0) {
+            if (active) ++n_visit;
+            if ((threadIdx.x & 31) == 0) ++n_wvisit;  // nodes the WARP visits: union of its lanes' paths
+        }
         if (c.kind == -2) {  // zero mass: skip the subtree (tree.rs:1087-1090)
             idx = c.next_branch;
             continue;
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
             atomicAdd(a.counters + 1, (unsigned long long)n_accept);
             atomicAdd(a.counters + 2, (unsigned long long)n_leaf);
             atomicAdd(a.counters + 3, (unsigned long long)n_leafp);
+            atomicAdd(a.counters + 4, (unsigned long long)n_wvisit);
         }
         return;
     }
@@ -463,11 +467,11 @@ extern "C" int pnbx_tree_eval(pnbx_tree* tp, const double* tgt_pos, int64_t m, i
 
 // Traversal statistics of the walk tree.rs:1069-1370 would do for these targets: totals over all targets of
 // node visits, accepted nodes, leaf visits and leaf particles (the oracle's counters; input to the work model
-// of BASELINE.md §3). One extra decisions-only kernel; results are exact integers.
+// of BASELINE.md §3), plus out5[4] = nodes visited per WARP summed over warps (union of 32 paths: the walk's real cost). One extra decisions-only kernel; results are exact integers.
 extern "C" int pnbx_tree_walk_counters(pnbx_tree* tp, const double* tgt_pos, int64_t m, int64_t tgt_begin, double theta,
-                                       int64_t* out4, const pnbx_opts* opts) {
+                                       int64_t* out5, const pnbx_opts* opts) {
     return guarded([&] {
-        if (!tp || !out4) throw ArgError{PNBX_ERR_ARG, "NULL argument"};
+        if (!tp || !out5) throw ArgError{PNBX_ERR_ARG, "NULL argument"};
         auto& t = *reinterpret_cast<pnbx_tree_impl*>(tp);
         if (!t.has_payload) throw ArgError{PNBX_ERR_STATE, "mass payload not built; call build_mass() before compute"};
         const bool self = tgt_pos == nullptr;
@@ -477,15 +481,15 @@ extern "C" int pnbx_tree_walk_counters(pnbx_tree* tp, const double* tgt_pos, int
         if (o.device < 0) o.device = t.device;
         Exec ex = make_exec(&o);
         StageTimer tm(ex.stream);
-        DevBuf<unsigned long long> cnt(4, ex.stream);
-        PNBX_CUDA(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(unsigned long long), ex.stream));
+        DevBuf<unsigned long long> cnt(5, ex.stream);
+        PNBX_CUDA(cudaMemsetAsync(cnt.p, 0, 5 * sizeof(unsigned long long), ex.stream));
         InArray<double> i_tgt;
         if (!self) i_tgt.bind(tgt_pos, (size_t)3 * m, ex);
         if (m > 0) tree_walk(t, ex, self ? nullptr : i_tgt.d, m, tgt_begin, theta, 1, nullptr, nullptr, tm, cnt.p);
-        unsigned long long h[4];
+        unsigned long long h[5];
         PNBX_CUDA(cudaMemcpyAsync(h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, ex.stream));
         PNBX_CUDA(cudaStreamSynchronize(ex.stream));
-        for (int i = 0; i < 4; ++i) out4[i] = (int64_t)h[i];
+        for (int i = 0; i < 5; ++i) out5[i] = (int64_t)h[i];
         finish_exec(ex);
     });
 }

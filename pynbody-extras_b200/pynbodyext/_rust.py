@@ -308,10 +308,11 @@ class Octree:
         (decisions-only pass; equals the oracle's counters). Not in the reference."""
         tgt = None if points is None else _vec3(points, "points")
         m = (self._n if count is None else int(count)) if tgt is None else tgt.shape[0]
-        out = np.zeros(4, dtype=np.int64)
+        out = np.zeros(5, dtype=np.int64)
         o = _opts(self._device, None)
         _check(_load().pnbx_tree_walk_counters(self._h, _ptr(tgt), m, int(tgt_begin), float(theta), _ptr(out), C.byref(o)))
-        return dict(zip(("visits", "accepts", "leaf_visits", "leaf_particles"), out.tolist()))
+        d = dict(zip(("visits", "accepts", "leaf_visits", "leaf_particles", "warp_visits"), out.tolist()))
+        return d
 
     # -- introspection used by the parity tests (not in the reference)
     def info(self) -> dict:

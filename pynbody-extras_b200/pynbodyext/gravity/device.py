@@ -143,7 +143,7 @@ class OctreeDevice:
 
     def walk_counters(self, theta, tgt_begin=0, count=None, tree_order=False, shard=None):
         import numpy as np
-        out = np.zeros(4, dtype=np.int64)
+        out = np.zeros(5, dtype=np.int64)
         o = _b._opts(self._dev.index, None)
         if tree_order:
             o.flags |= FLAG_TREE_ORDER
@@ -151,7 +151,8 @@ class OctreeDevice:
         m = ms if ms is not None else (self._n - tgt_begin if count is None else int(count))
         _b._check(_b._load().pnbx_tree_walk_counters(self._h, None, m, int(tgt_begin), float(theta), out.ctypes.data,
                                                      C.byref(o)))
-        return dict(zip(("visits", "accepts", "leaf_visits", "leaf_particles"), out.tolist()))
+        d = dict(zip(("visits", "accepts", "leaf_visits", "leaf_particles", "warp_visits"), out.tolist()))
+        return d
 
 
 def last_kernel_ms() -> float:

@@ -275,10 +275,12 @@ def test_walk_counters_equal_oracle_counters():
     o = O.Tree(pos, m, 8, 3, h, 1)
     for theta in (0.5, 0.7, 1.0):
         _, _, c_o = o.eval(theta, want=1, counters=True)
-        assert g.walk_counters(theta) == c_o
+        c_g = g.walk_counters(theta)
+        assert {k: c_g[k] for k in c_o} == c_o and c_g["warp_visits"] * 32 >= c_g["visits"]
     q, _ = plummer(3000, seed=82, a=3.0)
     _, _, c_o = o.eval(0.7, targets=q, want=1, counters=True)
-    assert g.walk_counters(0.7, points=q) == c_o
+    c_g = g.walk_counters(0.7, points=q)
+    assert {k: c_g[k] for k in c_o} == c_o
 
 
 def test_device_tree_api_matches_host_api():
@@ -350,7 +352,9 @@ def test_zero_mass_particles_and_nodes():
     assert rms_rel(p, p_o) < TOL64 and rms_rel_vec(a, a_o) < TOL64
     p, a = g._eval(None, 0.7, 3)
     assert rms_rel(p, p_o) < TOL32 and rms_rel_vec(a, a_o) < TOL32
-    assert g.walk_counters(0.7) == o.eval(0.7, want=1, counters=True)[2]
+    c_o = o.eval(0.7, want=1, counters=True)[2]
+    c_g = g.walk_counters(0.7)
+    assert {k: c_g[k] for k in c_o} == c_o
 
 
 def test_negative_and_zero_softenings_follow_reference_clamps():
