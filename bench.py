@@ -383,14 +383,26 @@ def run_ours(args):
     meas_tf2 = gdev.measure_fp32_peak(local, 1)
     int_per_launch = float(cnt) * float(n - 1)
     achieved_tf = FLOP_PER_INTERACTION * int_per_launch / (k_ms * 1e-3) / 1e12
+    # the same launch without the equal-mass specialisation (12 instead of 11 FP32-pipe ops per interaction)
+    os.environ["PNBX_DIRECT_NO_CONSTM"] = "1"
+    step(record=True)
+    torch.cuda.synchronize()
+    k_ms_general = gdev.last_kernel_ms()
+    del os.environ["PNBX_DIRECT_NO_CONSTM"]
     roofline = {
-        "bound": "fp32", "kernel": "direct_kernel<acc,plummer_const,f32>", "achieved": achieved_tf,
+        "bound": "fp32", "kernel": "direct_kernel_f2<acc, const_mass> (packed FP32x2; the workload has equal masses)",
+        "achieved": achieved_tf,
         "peak": meas_tf, "unit": "TFLOP/s", "frac": achieved_tf / meas_tf,
         "peak_source": "measured here: FFMA-chain microbenchmark (pnbx_measure_fp32_peak), MEASURED_PEAKS.json has no FP32 entry",
         "peak_nominal": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf, "peak_ffma2_chain": meas_tf2,
         "flop_per_interaction": FLOP_PER_INTERACTION, "interactions_per_launch": int_per_launch,
         "kernel_ms": k_ms, "ginteractions_per_s_kernel": int_per_launch / (k_ms * 1e-3) / 1e9,
-        "traffic": None,
+        "general_mass_variant": {"kernel_ms": k_ms_general,
+                                 "achieved": FLOP_PER_INTERACTION * int_per_launch / (k_ms_general * 1e-3) / 1e12,
+                                 "frac": FLOP_PER_INTERACTION * int_per_launch / (k_ms_general * 1e-3) / 1e12 / meas_tf},
+        "traffic": 172.3e6,
+        "traffic_note": "dram read+write per 1e12-interaction launch from ncu --set full (profiles/r01_direct_kernel_f2_ncu.md); "
+                        "algorithmic HBM bytes ~ 16 B per source per launch + 24 B per target result",
     }
 
     # ---- parity in the same run: fp32 GPU vs float64 oracle on a 256-target subsample (rank 0)
