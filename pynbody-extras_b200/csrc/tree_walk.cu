@@ -157,6 +157,9 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
                 if (sizeof(T) == 4) {  // fp32 sources are stored relative to their leaf's COM
                     lx = (T)(tx - gm.com[0]); ly = (T)(ty - gm.com[1]); lz = (T)(tz - gm.com[2]);
                 }
+                // Pass 1, branch-free: every pair as Newtonian / Plummer. For the spline kernel pairs with r < h
+                // (rare: the target's own and touching leaves) are only flagged here ...
+                bool inside = false;
                 for (int p = c.first; p < c.first + c.kind; ++p) {
                     Vec4T<T> s = load_src<T>(a, p);
                     const T dx = s.x - lx, dy = s.y - ly, dz = s.z - lz;
@@ -165,27 +168,45 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
                         s.w = T(0);
                         r2 = T(1);
                     }
-                    T h = T(0);
-                    if (soft) h = max(max(a.src_h[p], T(0)), th);  // tree.rs:234-235
-                    T kpot, g;
-                    if (spline && h > T(0) && r2 < h * h) {  // tree.rs:237-243 / 367-378
-                        const T rinv = mp::inv_sqrt<T>(r2 + tiny_v<T>());
-                        const T hinv = T(1) / h;
-                        const T u = (r2 + tiny_v<T>()) * rinv * hinv;
-                        kpot = w2_in(u) * hinv;
-                        g = w2p_in(u) * (hinv * hinv) * rinv;
-                    } else {
-                        if (!spline) r2 = fma(h, h, r2);  // Plummer: -1/sqrt(r^2+h^2), h = 0 is Newtonian
-                        const T rinv = mp::inv_sqrt<T>(r2 + tiny_v<T>());
-                        kpot = -rinv;
-                        g = rinv * rinv * rinv;
+                    if (soft) {
+                        const T h = max(max(a.src_h[p], T(0)), th);  // tree.rs:234-235
+                        if (spline) {
+                            const bool in = r2 < h * h;  // h > 0 is implied by r2 >= 0
+                            inside |= in;
+                            if (in) s.w = T(0);          // left to pass 2 (no add-then-subtract cancellation)
+                        } else {
+                            r2 = fma(h, h, r2);          // Plummer: -1/sqrt(r^2+h^2); h = 0 is Newtonian
+                        }
                     }
-                    if (WANT & PNBX_WANT_POT) pot = fma(s.w, kpot, pot);
+                    const T rinv = mp::inv_sqrt<T>(r2 + tiny_v<T>());
+                    const T mr = s.w * rinv;
+                    if (WANT & PNBX_WANT_POT) pot -= mr;
                     if (WANT & PNBX_WANT_ACC) {
-                        const T mg = s.w * g;
+                        const T mg = mr * (rinv * rinv);
                         ax = fma(dx, mg, ax);
                         ay = fma(dy, mg, ay);
                         az = fma(dz, mg, az);
+                    }
+                }
+                // ... and pass 2 adds their W2-kernel terms (tree.rs:237-243 / 367-378)
+                if (spline && inside) {
+                    for (int p = c.first; p < c.first + c.kind; ++p) {
+                        if (p == skip) continue;
+                        const Vec4T<T> s = load_src<T>(a, p);
+                        const T h = max(max(a.src_h[p], T(0)), th);
+                        const T dx = s.x - lx, dy = s.y - ly, dz = s.z - lz;
+                        const T r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                        if (!(r2 < h * h)) continue;
+                        const T rinv = mp::inv_sqrt<T>(r2 + tiny_v<T>());
+                        const T hinv = T(1) / h;
+                        const T u = (r2 + tiny_v<T>()) * rinv * hinv;
+                        if (WANT & PNBX_WANT_POT) pot = fma(s.w, w2_in(u) * hinv, pot);
+                        if (WANT & PNBX_WANT_ACC) {
+                            const T mg = s.w * (w2p_in(u) * (hinv * hinv) * rinv);
+                            ax = fma(dx, mg, ax);
+                            ay = fma(dy, mg, ay);
+                            az = fma(dz, mg, az);
+                        }
                     }
                 }
                 if (WANT & PNBX_WANT_POT) P += (double)pot;
@@ -195,22 +216,17 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
             continue;
         }
         // ---- internal node: per-lane opening decision in float64 (tree.rs:1114-1126)
-        bool accept = false;
-        double dx = 0, dy = 0, dz = 0;
-        if (active) {
-            dx = gm.com[0] - tx;
-            dy = gm.com[1] - ty;
-            dz = gm.com[2] - tz;
-            // (+ R2_TINY of tree.rs:1117 can only matter for dist2 < 1e-300, where nothing is accepted anyway)
-            const double dist2 = fma(dx, dx, fma(dy, dy, __dmul_rn(dz, dz)));
-            bool soft_ok = true;
-            if (gated) soft_ok = dist2 > c.gate2 && dist2 > gate_t;  // dist2 > max(gates): node_soft_ok (tree.rs:55-71)
-            accept = soft_ok && gm.size2 < __dmul_rn(a.theta2, dist2);
-        }
-        const unsigned need_open = __ballot_sync(FULL, active && !accept);
+        // evaluated by every lane without a branch (parked lanes compute a value nobody uses: free under SIMT)
+        const double dx = gm.com[0] - tx, dy = gm.com[1] - ty, dz = gm.com[2] - tz;
+        // (+ R2_TINY of tree.rs:1117 can only matter for dist2 < 1e-300, where nothing is accepted anyway)
+        const double dist2 = fma(dx, dx, fma(dy, dy, __dmul_rn(dz, dz)));
+        bool accept = gm.size2 < __dmul_rn(a.theta2, dist2);
+        if (gated) accept = accept && dist2 > c.gate2 && dist2 > gate_t;  // dist2 > max(gates): node_soft_ok (tree.rs:55-71)
+        accept = accept && active;
+        const bool need_open = __any_sync(FULL, active && !accept);
         if (WANT == 0) {
-            if (active && accept) ++n_accept;
-        } else if (active && accept) {
+            if (accept) ++n_accept;
+        } else if (accept) {
             if (sizeof(T) == 4 && ORDER <= 3) {
                 // fp32, order <= 3: contracted closed forms (multipole.cuh m2p_fast)
                 float pot = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
@@ -256,7 +272,7 @@ __global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
             }
         }
         if (need_open) {
-            if (active && accept) {  // done with this subtree; wait for the warp at its next_branch
+            if (accept) {  // done with this subtree; wait for the warp at its next_branch
                 active = false;
                 resume = c.next_branch;
             }
