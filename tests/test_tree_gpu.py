@@ -121,7 +121,8 @@ def test_self_eval_matches_oracle_tree(order):
         assert rms_rel(p64, p_o) < TOL64 and rms_rel_vec(a64, a_o) < TOL64
         p32, a32 = g._eval(None, theta, 3)
         assert rms_rel(p32, p_o) < TOL32 and rms_rel_vec(a32, a_o) < TOL32
-        assert np.array_equal(g.compute_potentials(theta), p32) and np.array_equal(g.compute_accelerations(theta), a32)
+        # the fused (pot+acc) and single-output kernels may contract multiply-adds differently: fp32 rounding level
+        assert rms_rel(g.compute_potentials(theta), p32) < 1e-6 and rms_rel_vec(g.compute_accelerations(theta), a32) < 1e-6
 
 
 @pytest.mark.parametrize("order", [0, 3, 5])
