@@ -17,7 +17,13 @@
 namespace pnbx {
 namespace {
 
-constexpr int WT = 128;  // threads per block (4 independent warps)
+#ifndef PNBX_WT
+#define PNBX_WT 128
+#endif
+#ifndef PNBX_WALK_MINB
+#define PNBX_WALK_MINB 12  // 40 registers: 48 of 64 warps resident (measured best for potentials, profiles/)
+#endif
+constexpr int WT = PNBX_WT;  // threads per block (independent warps)
 
 template <class T>
 struct Vec4T {
@@ -92,7 +98,7 @@ __device__ __forceinline__ Vec4T<double> load_src<double>(const WalkArgs<double>
 //        3 = decided at run time (float64 verification mode and the counting pass).
 // WANT == 0 is the counting pass: traversal decisions only, totals into a.counters.
 template <int ORDER, int WANT, class T, int SMODE>
-__global__ void __launch_bounds__(WT) walk_kernel(const WalkArgs<T> a) {
+__global__ void __launch_bounds__(WT, PNBX_WALK_MINB) walk_kernel(const WalkArgs<T> a) {
     constexpr int DORD = (WANT & PNBX_WANT_ACC) ? (ORDER < 1 ? 1 : ORDER) : (ORDER < 2 ? 0 : ORDER);
     constexpr unsigned FULL = 0xffffffffu;
     const int64_t k = (int64_t)blockIdx.x * WT + threadIdx.x;
