@@ -21,6 +21,7 @@ import sys
 import tempfile
 import time
 
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")  # idle OpenMP workers of the CPU oracle must not spin
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (os.path.join(ROOT, "pynbody-extras_b200"), ROOT):
     if p not in sys.path:
@@ -240,20 +241,29 @@ def tree_section(args, rank, world, local, dev, barrier, peak_tf):
                       "h2d_bytes_per_step": int(pos.nbytes + mass.nbytes + h.nbytes), "d2h_bytes_per_step": int(out.nbytes),
                       "api": "Gravity(pos, mass, softening=h, kernel=Spline).tree_potentials(theta=0.7) (construct + walk), "
                              "pinned host arrays"}
-        if not args.no_cpu:
-            from oracle import oracle as O
-            ns = min(n, 1_000_000)  # bounded CPU sample: the reference's serial build is ~1 s per 1e6 particles
-            t0 = time.perf_counter()
-            ot = O.Tree(pos[:ns], mass[:ns], leaf, order, h[:ns], 1)
-            tb = time.perf_counter() - t0
-            t0 = time.perf_counter()
-            ot.eval(theta, want=1)
-            tw = time.perf_counter() - t0
-            res["cpu_baseline"] = {"value": ns / (tb + tw), "unit": "particles/s", "cores": O.num_threads(), "kind": "port",
-                                   "sample": f"first {ns} particles of the same set: construct {tb:.2f} s (serial, as the "
-                                             f"reference) + potentials {tw:.2f} s (OpenMP)"}
     del tree
     return res
+
+
+def tree_cpu_baseline(args):
+    """CPU oracle on a bounded sample of the tree workload (the reference's build is serial: ~0.6 s per 1e6)."""
+    from benchmarks.synthetic import nfw_disc
+    from oracle import oracle as O
+    try:
+        O.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    ns = min(args.tree_n, 1_000_000)
+    pos, mass, h = nfw_disc(ns, seed=3)
+    t0 = time.perf_counter()
+    ot = O.Tree(pos, mass, 8, 3, h, 1)
+    tb = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ot.eval(0.7, want=1)
+    tw = time.perf_counter() - t0
+    return {"value": ns / (tb + tw), "unit": "particles/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"NFW+disc N={ns} (same generator, seed 3): construct {tb:.2f} s (serial, as the reference) + "
+                      f"potentials {tw:.2f} s (OpenMP), theta 0.7, order 3, leaf 8"}
 
 
 def run_reference(args):
@@ -448,13 +458,16 @@ def run_ours(args):
            "api": "Gravity(...).direct_accelerations() with pinned host numpy arrays" if world == 1
                   else "pynbodyext.gravity.sharded.direct_sharded (per-rank shard H2D, NCCL all-gather, D2H)"}
 
-    if rank == 0 and world == 1 and not args.no_cpu:
-        r, cores, sample = cpu_reference_rate(pos, mass, 12.0)
-        cpu = {"value": r / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-
     tree = None
     if not args.no_tree:
         tree = tree_section(args, rank, world, local, dev, barrier, meas_tf)
+
+    # CPU legs last: the oracle's OpenMP team must not compete with the host side of the GPU measurements above
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r, cores, sample = cpu_reference_rate(pos, mass, 12.0)
+        cpu = {"value": r / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        if tree is not None:
+            tree["cpu_baseline"] = tree_cpu_baseline(args)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
