@@ -92,3 +92,41 @@ def test_compute_fails_loudly_without_a_gpu():
     from pynbodyext.gravity import Gravity
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Gravity(pos, np.ones(16)).tree_potentials()
+
+
+def test_capi_argument_validation_without_gpu():
+    # argument errors are reported before any device work: status code + thread-local message through the C-ABI
+    import ctypes as C
+
+    import numpy as np
+    import pynbodyext._rust as r
+
+    lib = r._load()
+    pos = np.zeros((4, 3))
+    out = np.zeros(4)
+    o = r._opts()
+    p = lambda a: a.ctypes.data  # noqa: E731
+    # bad `want`
+    rc = lib.pnbx_direct(p(pos), None, None, 4, None, 4, 0, -1, 0, p(out), None, C.byref(o))
+    assert rc == r.PNBX_ERR_ARG and b"want" in lib.pnbx_last_error()
+    # missing output buffer
+    rc = lib.pnbx_direct(p(pos), None, None, 4, None, 4, 0, -1, 1, None, None, C.byref(o))
+    assert rc == r.PNBX_ERR_ARG and b"out_pot" in lib.pnbx_last_error()
+    # shard outside [0, N)
+    rc = lib.pnbx_direct(p(pos), None, None, 4, None, 3, 2, -1, 1, p(out), None, C.byref(o))
+    assert rc == r.PNBX_ERR_ARG and b"shard" in lib.pnbx_last_error()
+    # softenings without kernel / bad kernel code (gravity.rs:71-73, 480-484)
+    rc = lib.pnbx_direct(p(pos), None, p(out), 4, None, 4, 0, -1, 1, p(out), None, C.byref(o))
+    assert rc == r.PNBX_ERR_ARG and b"softenings require an explicit kernel" in lib.pnbx_last_error()
+    rc = lib.pnbx_direct(p(pos), None, None, 4, None, 4, 0, 7, 1, p(out), None, C.byref(o))
+    assert rc == r.PNBX_ERR_ARG and b"kernel must be 0 (Plummer) or 1 (CubicSplineW2)" in lib.pnbx_last_error()
+    # tree: bad kernel, NULL handle
+    h = C.c_void_p()
+    rc = lib.pnbx_tree_create(C.byref(h), p(pos), None, None, 4, 8, 0, 5, C.byref(o))
+    assert rc == r.PNBX_ERR_ARG and not h.value
+    assert lib.pnbx_tree_set_kernel(None, 0) == r.PNBX_ERR_ARG
+    lib.pnbx_shard_count.restype = C.c_int64
+    lib.pnbx_shard_count.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32]
+    n = 100_003
+    assert sum(lib.pnbx_shard_count(n, 4096, 8, k) for k in range(8)) == n
+    assert lib.pnbx_shard_count(n, 4096, 1, 0) == n and lib.pnbx_shard_count(n, 4096, 8, 9) == 0

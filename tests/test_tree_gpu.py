@@ -375,3 +375,36 @@ def test_negative_and_zero_softenings_follow_reference_clamps():
         p = r.direct_potentials_py(pos, m, 0, h, kernel, precision="f64")
         a = r.direct_accelerations_py(pos, m, 0, h, kernel, precision="f64")
         assert rms_rel(p, p_d) < TOL64 and rms_rel_vec(a, a_d) < TOL64
+
+
+def test_concurrent_queries_on_one_tree_from_threads():
+    # compute methods take &self in the reference and release the GIL (gravity.rs:103-111, 267-444): concurrent
+    # queries on one Octree from several Python threads are legal; here every thread gets its own stream + temporaries
+    import threading
+    r = R()
+    pos, m = hernquist(40000, seed=111)
+    g = r.Octree(pos, m, 8, 3, np.full(40000, 0.01), 1)
+    ref_p = g.compute_potentials(0.7)
+    ref_a = g.compute_accelerations(0.6)
+    q = pos[:5000] * 1.01
+    ref_q = g.potentials_at_points(q, 0.7)
+    out, errs = {}, []
+
+    def work(k):
+        try:
+            for _ in range(3):
+                if k % 3 == 0:
+                    out[k] = np.array_equal(g.compute_potentials(0.7), ref_p)
+                elif k % 3 == 1:
+                    out[k] = np.array_equal(g.compute_accelerations(0.6), ref_a)
+                else:
+                    out[k] = np.array_equal(g.potentials_at_points(q, 0.7), ref_q)
+        except Exception as exc:  # pragma: no cover
+            errs.append(exc)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(6)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs and all(out[k] for k in range(6))
