@@ -165,6 +165,50 @@ __device__ __forceinline__ void interact(T xi, T yi, T zi, T e, const Vec4<T>& s
     }
 }
 
+// Cubic-spline fast path, pass 1: the pair as Newtonian unless it lies inside the softening (r < h), in which case
+// it contributes nothing here and `inside` is raised; pass 2 (spline_inside) adds the W2 terms of those rare pairs.
+template <int WANT, class T>
+__device__ __forceinline__ void spline_outside(T xi, T yi, T zi, T hi, const Vec4<T>& s, T hj, bool& inside, T& ax,
+                                               T& ay, T& az, T& pot) {
+    const T dx = s.x - xi, dy = s.y - yi, dz = s.z - zi;
+    const T h = tmax(hi, hj);
+    T r2 = fma(dx, dx, tiny<T>());
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
+    const bool in = h > T(0) && r2 < h * h;  // kernel.rs:46-54, 72-80
+    inside |= in;
+    const T m = in ? T(0) : s.w;
+    const T rinv = rsqrt_fast(r2);
+    const T mr = m * rinv;
+    if (WANT & PNBX_WANT_POT) pot -= mr;
+    if (WANT & PNBX_WANT_ACC) {
+        const T g = mr * (rinv * rinv);
+        ax = fma(dx, g, ax);
+        ay = fma(dy, g, ay);
+        az = fma(dz, g, az);
+    }
+}
+template <int WANT, class T>
+__device__ __forceinline__ void spline_inside(T xi, T yi, T zi, T hi, const Vec4<T>& s, T hj, T& ax, T& ay, T& az,
+                                              T& pot) {
+    const T dx = s.x - xi, dy = s.y - yi, dz = s.z - zi;
+    const T h = tmax(hi, hj);
+    T r2 = fma(dx, dx, tiny<T>());
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
+    if (!(h > T(0) && r2 < h * h)) return;
+    const T rinv = rsqrt_fast(r2);
+    const T hinv = T(1) / h;
+    const T u = (r2 * rinv) * hinv;
+    if (WANT & PNBX_WANT_POT) pot = fma(s.w, w2_inner(u) * hinv, pot);
+    if (WANT & PNBX_WANT_ACC) {
+        const T mg = s.w * (w2p_inner(u) * (hinv * hinv) * rinv);
+        ax = fma(dx, mg, ax);
+        ay = fma(dy, mg, ay);
+        az = fma(dz, mg, az);
+    }
+}
+
 template <int WANT, int SOFT, class T, int TILE>
 __global__ void __launch_bounds__(DT, PNBX_MINB)
 direct_kernel(const Vec4<T>* __restrict__ src, const T* __restrict__ src_h, int64_t n_src,
@@ -234,7 +278,28 @@ direct_kernel(const Vec4<T>* __restrict__ src, const T* __restrict__ src_h, int6
         for (int k = 0; k < TPT; ++k) ax[k] = ay[k] = az[k] = p[k] = T(0);
 
         const bool diag = (j0 < blk_hi) && (j0 + cnt > blk_lo);  // tile holds some of this block's own particles
-        if (!diag && cnt == TILE) {
+        if (!diag && cnt == TILE && SOFT == SOFT_SPLINE) {
+            // two passes: branch-free Newtonian sweep, then (only if some lane of the warp saw a pair with r < h,
+            // which is rare) a second sweep of the tile that adds the W2-kernel terms of exactly those pairs
+            bool inside = false;
+#pragma unroll 8
+            for (int j = 0; j < TILE; ++j) {
+                const Vec4<T> s = s_src[st][j];
+                const T hj = s_h[st][j];
+#pragma unroll
+                for (int k = 0; k < TPT; ++k) spline_outside<WANT, T>(xi[k], yi[k], zi[k], ei[k], s, hj, inside, ax[k], ay[k], az[k], p[k]);
+            }
+            if (__any_sync(0xffffffffu, inside)) {
+                if (inside) {
+                    for (int j = 0; j < TILE; ++j) {
+                        const Vec4<T> s = s_src[st][j];
+                        const T hj = s_h[st][j];
+#pragma unroll
+                        for (int k = 0; k < TPT; ++k) spline_inside<WANT, T>(xi[k], yi[k], zi[k], ei[k], s, hj, ax[k], ay[k], az[k], p[k]);
+                    }
+                }
+            }
+        } else if (!diag && cnt == TILE) {
 #pragma unroll 8
             for (int j = 0; j < TILE; ++j) {
                 Vec4<T> s = s_src[st][j];
