@@ -404,7 +404,9 @@ __device__ __forceinline__ void m2p_accel(const T* M, const T* D, T& ax, T& ay, 
 // C(u) = sum_{l+m+n=3} M_lmn u^lmn, w_x = 3 m300 + m120 + m102 (cyclic).
 // Per-node record (float): [0] M, [1..6] 6S (xx,yy,zz,xy,xz,yz), [7] 3 trS, [8..17] octupole (field order),
 // [18..20] 3w, [21..23] pad.  REC = 1 (order<=1), 8 (order 2), 24 (order 3).
-__host__ __device__ constexpr int fast_rec_floats(int order) { return order <= 1 ? 1 : order == 2 ? 8 : 24; }
+__host__ __device__ constexpr int fast_rec_floats(int order) {
+    return order <= 1 ? 1 : order == 2 ? 8 : order == 3 ? 24 : order == 4 ? 48 : 84;
+}
 
 template <int ORDER, int WANT>
 __device__ __forceinline__ void m2p_fast(const float* __restrict__ rec, float dx, float dy, float dz, float& pot,
@@ -467,6 +469,112 @@ __device__ __forceinline__ void m2p_fast(const float* __restrict__ rec, float dx
             az = fmaf(ri4, fmaf(c1, uz, -qz), az);
         }
     }
+}
+
+// ---- fp32 fast M2P for orders 4 and 5 ------------------------------------------------------------
+// For a homogeneous polynomial P_p(d) = sum_{|n|=p} M_n d^n the tensor contraction collapses to
+//   sum_n M_n D_n(d) = sum_k c_{p,k} (Lap^k P_p)(d) / r^(2p+1-2k),   c_{p,k} = (-1)^(p-k) (2p-2k-1)!! / (2^k k!),
+// (checked against the reference's d_lmn for p = 2, 3, 4), so with u = d/r:
+//   Psi_2 = (3 S(u,u) - trS) / r^3                        Psi_3 = (-15 C(u) + 9 v.u) / r^4
+//   Psi_4 = (105 Q(u) - 7.5 LapQ(u) + 0.375 Lap2Q) / r^5   Psi_5 = (-945 R(u) + 52.5 LapR(u) - 1.875 Lap2R.u) / r^6
+//   phi = -(M/r + Psi_2 + ... + Psi_order)                  a = -grad_d (M/r + Psi_2 + ... + Psi_(order-1))
+// The Laplacians' coefficients are precomputed per node (pack_walk_moments). Record (floats): [0..23] the order-3 record,
+// [24..38] Q (m400..m112, field order), [39..44] LapQ as a quadratic form (xx,yy,zz,xy,xz,yz), [45] Lap2Q, [46,47] pad,
+// [48..68] R (m500..m113), [69..78] LapR as a cubic (x3,y3,z3,x2y,x2z,xy2,xz2,y2z,yz2,xyz), [79..81] Lap2R, [82,83] pad.
+template <int ORDER, int WANT>
+__device__ __forceinline__ void m2p_fast45(const float* __restrict__ rec, float dx, float dy, float dz, float& pot,
+                                           float& ax, float& ay, float& az) {
+    static_assert(ORDER == 4 || ORDER == 5, "orders 4 and 5 only");
+    float r[ORDER == 4 ? 48 : 84];
+    constexpr int NV = (ORDER == 4 ? 48 : 84) / 4;
+    constexpr int NEED = (WANT & 1) ? NV : (ORDER == 4 ? 6 : 12);  // acc-only needs the records of order-1 moments
+#pragma unroll
+    for (int v = 0; v < NEED; ++v) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(rec) + v);
+        r[4 * v] = q.x; r[4 * v + 1] = q.y; r[4 * v + 2] = q.z; r[4 * v + 3] = q.w;
+    }
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, FLT_MIN)));
+    const float ri = inv_sqrt<float>(r2);
+    const float ri2 = ri * ri, ri3 = ri2 * ri, ri4 = ri2 * ri2, ri5 = ri4 * ri, ri6 = ri4 * ri2;
+    const float a = dx * ri, b = dy * ri, c = dz * ri;
+    const float a2 = a * a, b2 = b * b, c2 = c * c, ab = a * b, ac = a * c, bc = b * c;
+    const float M = r[0];
+    // quadrupole: q6 = 6 S u, s6 = 6 S(u,u), tr3 = 3 trS
+    const float qx = fmaf(r[5], c, fmaf(r[4], b, r[1] * a));
+    const float qy = fmaf(r[6], c, fmaf(r[2], b, r[4] * a));
+    const float qz = fmaf(r[3], c, fmaf(r[6], b, r[5] * a));
+    const float s6 = fmaf(qz, c, fmaf(qy, b, qx * a));
+    const float tr3 = r[7];
+    // octupole: gradient of the cubic form C(u) (C = u.gradC / 3), w3 = 9 v
+    const float m300 = r[8], m030 = r[9], m003 = r[10], m210 = r[11], m201 = r[12], m120 = r[13], m102 = r[14],
+                m021 = r[15], m012 = r[16], m111 = r[17];
+    const float gCx = fmaf(3.f * m300, a2, fmaf(2.f * m210, ab, fmaf(2.f * m201, ac, fmaf(m120, b2, fmaf(m102, c2, m111 * bc)))));
+    const float gCy = fmaf(3.f * m030, b2, fmaf(2.f * m120, ab, fmaf(2.f * m021, bc, fmaf(m210, a2, fmaf(m012, c2, m111 * ac)))));
+    const float gCz = fmaf(3.f * m003, c2, fmaf(2.f * m102, ac, fmaf(2.f * m012, bc, fmaf(m201, a2, fmaf(m021, b2, m111 * ab)))));
+    const float C3 = fmaf(gCz, c, fmaf(gCy, b, gCx * a));                 // 3 C(u)
+    const float wu3 = fmaf(r[20], c, fmaf(r[19], b, r[18] * a));          // 9 v.u
+    float phi = 0.f;
+    if (WANT & 1) {
+        phi = -M * ri;
+        phi = fmaf(-ri3, fmaf(0.5f, s6, -(1.f / 3.f) * tr3), phi);        // -Psi_2
+        phi = fmaf(ri4, fmaf(5.f, C3, -wu3), phi);                        // -Psi_3 = (15 C - 9 v.u)/r^4
+    }
+    if (WANT & 2) {
+        const float g = M * ri3;
+        ax = g * dx; ay = g * dy; az = g * dz;
+        const float c1 = fmaf(2.5f, s6, -tr3);                            // -grad Psi_2
+        ax = fmaf(ri4, fmaf(c1, a, -qx), ax);
+        ay = fmaf(ri4, fmaf(c1, b, -qy), ay);
+        az = fmaf(ri4, fmaf(c1, c, -qz), az);
+        // -grad Psi_3 = [15 gradC - 105 C u - 9 v + 45 (v.u) u] / r^5
+        const float c3 = fmaf(-35.f, C3, 5.f * wu3);                      // -105 C + 45 v.u
+        ax = fmaf(ri5, fmaf(15.f, gCx, fmaf(c3, a, -r[18])), ax);
+        ay = fmaf(ri5, fmaf(15.f, gCy, fmaf(c3, b, -r[19])), ay);
+        az = fmaf(ri5, fmaf(15.f, gCz, fmaf(c3, c, -r[20])), az);
+    }
+    if ((WANT & 1) || ORDER == 5) {
+        // hexadecapole: gradient of the quartic form Q(u) (Q = u.gradQ / 4), LapQ(u) and its gradient, Lap2Q
+        const float m400 = r[24], m040 = r[25], m004 = r[26], m310 = r[27], m301 = r[28], m130 = r[29], m103 = r[30],
+                    m031 = r[31], m013 = r[32], m220 = r[33], m202 = r[34], m022 = r[35], m211 = r[36], m121 = r[37],
+                    m112 = r[38];
+        const float a3 = a2 * a, b3 = b2 * b, c3p = c2 * c;
+        const float gQx = 4.f * m400 * a3 + 3.f * (m310 * a2 * b + m301 * a2 * c) + m130 * b3 + m103 * c3p +
+                          2.f * a * (m220 * b2 + m202 * c2 + m211 * bc) + bc * (m121 * b + m112 * c);
+        const float gQy = 4.f * m040 * b3 + 3.f * (m130 * a * b2 + m031 * b2 * c) + m310 * a3 + m013 * c3p +
+                          2.f * b * (m220 * a2 + m022 * c2 + m121 * ac) + ac * (m211 * a + m112 * c);
+        const float gQz = 4.f * m004 * c3p + 3.f * (m103 * a * c2 + m013 * b * c2) + m301 * a3 + m031 * b3 +
+                          2.f * c * (m202 * a2 + m022 * b2 + m112 * ab) + ab * (m211 * a + m121 * b);
+        const float Q4 = fmaf(gQz, c, fmaf(gQy, b, gQx * a));             // 4 Q(u)
+        const float Lxx = r[39], Lyy = r[40], Lzz = r[41], Lxy = r[42], Lxz = r[43], Lyz = r[44], L2 = r[45];
+        const float gLx = fmaf(2.f * Lxx, a, fmaf(Lxy, b, Lxz * c));      // grad LapQ
+        const float gLy = fmaf(2.f * Lyy, b, fmaf(Lxy, a, Lyz * c));
+        const float gLz = fmaf(2.f * Lzz, c, fmaf(Lxz, a, Lyz * b));
+        const float LQ2 = fmaf(gLz, c, fmaf(gLy, b, gLx * a));            // 2 LapQ(u)
+        if (WANT & 1) phi = fmaf(-ri5, fmaf(26.25f, Q4, fmaf(-3.75f, LQ2, 0.375f * L2)), phi);  // -Psi_4
+        if ((WANT & 2) && ORDER == 5) {
+            // -grad Psi_4 = [-105 gradQ + 945 Q u + 7.5 gradLapQ - 52.5 LapQ u + 1.875 Lap2Q u] / r^6
+            const float c4 = fmaf(236.25f, Q4, fmaf(-26.25f, LQ2, 1.875f * L2));
+            ax = fmaf(ri6, fmaf(-105.f, gQx, fmaf(7.5f, gLx, c4 * a)), ax);
+            ay = fmaf(ri6, fmaf(-105.f, gQy, fmaf(7.5f, gLy, c4 * b)), ay);
+            az = fmaf(ri6, fmaf(-105.f, gQz, fmaf(7.5f, gLz, c4 * c)), az);
+        }
+    }
+    if ((WANT & 1) && ORDER == 5) {
+        // 32-pole: quintic form R(u), cubic LapR(u), linear Lap2R.u
+        const float* m = r + 48;  // m500 m050 m005 m410 m401 m140 m104 m041 m014 m320 m302 m230 m203 m032 m023 m221 m212 m122 m311 m131 m113
+        const float a3 = a2 * a, b3 = b2 * b, c3p = c2 * c, a4 = a2 * a2, b4 = b2 * b2, c4p = c2 * c2;
+        float R = m[0] * a4 * a + m[1] * b4 * b + m[2] * c4p * c;
+        R += a4 * (m[3] * b + m[4] * c) + b4 * (m[5] * a + m[7] * c) + c4p * (m[6] * a + m[8] * b);
+        R += a3 * (m[9] * b2 + m[10] * c2 + m[18] * bc) + b3 * (m[11] * a2 + m[13] * c2 + m[19] * ac) +
+             c3p * (m[12] * a2 + m[14] * b2 + m[20] * ab);
+        R += m[15] * a2 * b2 * c + m[16] * a2 * b * c2 + m[17] * a * b2 * c2;
+        const float* l = r + 69;  // x3 y3 z3 x2y x2z xy2 xz2 y2z yz2 xyz
+        const float LR = l[0] * a3 + l[1] * b3 + l[2] * c3p + a2 * (l[3] * b + l[4] * c) + b2 * (l[5] * a + l[7] * c) +
+                         c2 * (l[6] * a + l[8] * b) + l[9] * a * bc;
+        const float L2R = fmaf(r[81], c, fmaf(r[80], b, r[79] * a));
+        phi = fmaf(-ri6, fmaf(-945.f, R, fmaf(52.5f, LR, -1.875f * L2R)), phi);  // -Psi_5
+    }
+    if (WANT & 1) pot = phi;
 }
 
 }  // namespace mp

@@ -416,10 +416,6 @@ __global__ void pack_walk_moments(const double* __restrict__ mom, int64_t nn, in
     float* o = out + i * rec;
     using namespace mp;
     if (order <= 1) { o[0] = (float)m[I000]; return; }
-    if (order >= 4) {
-        for (int t = 0; t < rec; ++t) o[t] = t < K ? (float)m[t] : 0.f;
-        return;
-    }
     o[0] = (float)m[I000];
     o[1] = (float)(6.0 * m[I200]); o[2] = (float)(6.0 * m[I020]); o[3] = (float)(6.0 * m[I002]);
     o[4] = (float)(3.0 * m[I110]); o[5] = (float)(3.0 * m[I101]); o[6] = (float)(3.0 * m[I011]);
@@ -430,6 +426,36 @@ __global__ void pack_walk_moments(const double* __restrict__ mom, int64_t nn, in
         o[19] = (float)(3.0 * (3.0 * m[I030] + m[I210] + m[I012]));
         o[20] = (float)(3.0 * (3.0 * m[I003] + m[I201] + m[I021]));
         o[21] = o[22] = o[23] = 0.f;
+    }
+    if (order >= 4) {  // m2p_fast45 layout: octupole slots [18..20] hold 9 v = 3 w (same numbers as above)
+        for (int t = 0; t < 15; ++t) o[24 + t] = (float)m[I400 + t];
+        o[39] = (float)(12.0 * m[I400] + 2.0 * m[I220] + 2.0 * m[I202]);
+        o[40] = (float)(12.0 * m[I040] + 2.0 * m[I220] + 2.0 * m[I022]);
+        o[41] = (float)(12.0 * m[I004] + 2.0 * m[I202] + 2.0 * m[I022]);
+        o[42] = (float)(6.0 * m[I310] + 6.0 * m[I130] + 2.0 * m[I112]);
+        o[43] = (float)(6.0 * m[I301] + 6.0 * m[I103] + 2.0 * m[I121]);
+        o[44] = (float)(6.0 * m[I031] + 6.0 * m[I013] + 2.0 * m[I211]);
+        o[45] = (float)(24.0 * (m[I400] + m[I040] + m[I004]) + 8.0 * (m[I220] + m[I202] + m[I022]));
+        o[46] = o[47] = 0.f;
+    }
+    if (order >= 5) {
+        for (int t = 0; t < 21; ++t) o[48 + t] = (float)m[I500 + t];
+        const double x3 = 20.0 * m[I500] + 2.0 * m[I320] + 2.0 * m[I302];
+        const double y3 = 20.0 * m[I050] + 2.0 * m[I230] + 2.0 * m[I032];
+        const double z3 = 20.0 * m[I005] + 2.0 * m[I203] + 2.0 * m[I023];
+        const double x2y = 12.0 * m[I410] + 6.0 * m[I230] + 2.0 * m[I212];
+        const double x2z = 12.0 * m[I401] + 6.0 * m[I203] + 2.0 * m[I221];
+        const double xy2 = 12.0 * m[I140] + 6.0 * m[I320] + 2.0 * m[I122];
+        const double xz2 = 12.0 * m[I104] + 6.0 * m[I302] + 2.0 * m[I122];
+        const double y2z = 12.0 * m[I041] + 6.0 * m[I023] + 2.0 * m[I221];
+        const double yz2 = 12.0 * m[I014] + 6.0 * m[I032] + 2.0 * m[I212];
+        const double xyz = 6.0 * (m[I311] + m[I131] + m[I113]);
+        o[69] = (float)x3; o[70] = (float)y3; o[71] = (float)z3; o[72] = (float)x2y; o[73] = (float)x2z;
+        o[74] = (float)xy2; o[75] = (float)xz2; o[76] = (float)y2z; o[77] = (float)yz2; o[78] = (float)xyz;
+        o[79] = (float)(6.0 * x3 + 2.0 * xy2 + 2.0 * xz2);
+        o[80] = (float)(6.0 * y3 + 2.0 * x2y + 2.0 * yz2);
+        o[81] = (float)(6.0 * z3 + 2.0 * x2z + 2.0 * y2z);
+        o[82] = o[83] = 0.f;
     }
 }
 
@@ -644,7 +670,7 @@ void build_mass_payload(pnbx_tree_impl& t, cudaStream_t s, StageTimer& tm) {
         PNBX_LAUNCH(leaf_local_sources, nblk(nn), 256, 0, s, t.node_nchild.p, t.node_start.p, t.node_count.p, t.ncom.p,
                     t.spos.p, t.has_mass ? t.smass.p : nullptr, nn, t.src32.p);
     }
-    t.rec32 = t.order <= 3 ? mp::fast_rec_floats(t.order) : (t.n_moments + 3) / 4 * 4;
+    t.rec32 = mp::fast_rec_floats(t.order);
     t.moments32.alloc((size_t)nn * t.rec32, s);
     PNBX_LAUNCH(pack_walk_moments, nblk(nn), 256, 0, s, t.moments.p, nn, t.order, t.n_moments, t.rec32, t.moments32.p);
     PNBX_CUDA(cudaGetLastError());

@@ -233,11 +233,12 @@ __global__ void __launch_bounds__(WT, PNBX_WALK_MINB) walk_kernel(const WalkArgs
         if (WANT == 0) {
             if (accept) ++n_accept;
         } else if (accept) {
-            if (sizeof(T) == 4 && ORDER <= 3) {
-                // fp32, order <= 3: contracted closed forms (multipole.cuh m2p_fast)
+            if (sizeof(T) == 4) {
+                // fp32: contracted closed forms on the per-node fp32 record (multipole.cuh m2p_fast / m2p_fast45)
                 float pot = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-                mp::m2p_fast<ORDER, (WANT == 0 ? 1 : WANT)>(reinterpret_cast<const float*>(a.moments) + (int64_t)idx * a.K, (float)dx, (float)dy,
-                                          (float)dz, pot, ax, ay, az);
+                const float* rec = reinterpret_cast<const float*>(a.moments) + (int64_t)idx * a.K;
+                if (ORDER <= 3) mp::m2p_fast<(ORDER <= 3 ? ORDER : 3), (WANT == 0 ? 1 : WANT)>(rec, (float)dx, (float)dy, (float)dz, pot, ax, ay, az);
+                else mp::m2p_fast45<(ORDER >= 4 ? ORDER : 4), (WANT == 0 ? 1 : WANT)>(rec, (float)dx, (float)dy, (float)dz, pot, ax, ay, az);
                 if (WANT & PNBX_WANT_POT) P += (double)pot;
                 if (WANT & PNBX_WANT_ACC) { Ax += (double)ax; Ay += (double)ay; Az += (double)az; }
             } else {
@@ -254,20 +255,8 @@ __global__ void __launch_bounds__(WT, PNBX_WALK_MINB) walk_kernel(const WalkArgs
                     }
                 } else {
                     T Mr[mp::stored_coeffs(ORDER)];
-                    if (sizeof(T) == 4) {  // padded to a multiple of 4 floats: vector loads
-                        constexpr int NV = (mp::stored_coeffs(ORDER) + 3) / 4;
 #pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            const float4 q = __ldg(reinterpret_cast<const float4*>(M) + v);
-                            const float qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (4 * v + e < mp::stored_coeffs(ORDER)) Mr[4 * v + e] = (T)qq[e];
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < mp::stored_coeffs(ORDER); ++i) Mr[i] = M[i];
-                    }
+                    for (int i = 0; i < mp::stored_coeffs(ORDER); ++i) Mr[i] = M[i];
                     if (WANT & PNBX_WANT_POT) P += (double)mp::m2p_potential<ORDER, T>(Mr, D);
                     if (WANT & PNBX_WANT_ACC) {
                         T ax, ay, az;
