@@ -98,7 +98,7 @@ __device__ __forceinline__ Vec4T<double> load_src<double>(const WalkArgs<double>
 //        3 = decided at run time (float64 verification mode and the counting pass).
 // WANT == 0 is the counting pass: traversal decisions only, totals into a.counters.
 template <int ORDER, int WANT, class T, int SMODE>
-__global__ void __launch_bounds__(WT, PNBX_WALK_MINB) walk_kernel(const WalkArgs<T> a) {
+__global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_WALK_MINB) walk_kernel(const WalkArgs<T> a) {
     constexpr int DORD = (WANT & PNBX_WANT_ACC) ? (ORDER < 1 ? 1 : ORDER) : (ORDER < 2 ? 0 : ORDER);
     constexpr unsigned FULL = 0xffffffffu;
     const int64_t k = (int64_t)blockIdx.x * WT + threadIdx.x;

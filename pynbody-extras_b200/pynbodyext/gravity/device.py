@@ -87,9 +87,10 @@ class OctreeDevice:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h is not None and h.value and _b._lib is not None:
-            _b._lib.pnbx_tree_destroy(h)
-            self._h = C.c_void_p()
+        lib = getattr(_b, "_lib", None) if _b is not None else None  # module globals may be gone at interpreter exit
+        if h is not None and h.value and lib is not None:
+            lib.pnbx_tree_destroy(h)
+            self._h = None
 
     def info(self):
         inf = _b.pnbx_tree_info()
