@@ -508,10 +508,18 @@ __device__ __forceinline__ void m2p_fast45(const float* __restrict__ rec, float 
     // octupole: gradient of the cubic form C(u) (C = u.gradC / 3), w3 = 9 v
     const float m300 = r[8], m030 = r[9], m003 = r[10], m210 = r[11], m201 = r[12], m120 = r[13], m102 = r[14],
                 m021 = r[15], m012 = r[16], m111 = r[17];
-    const float gCx = fmaf(3.f * m300, a2, fmaf(2.f * m210, ab, fmaf(2.f * m201, ac, fmaf(m120, b2, fmaf(m102, c2, m111 * bc)))));
-    const float gCy = fmaf(3.f * m030, b2, fmaf(2.f * m120, ab, fmaf(2.f * m021, bc, fmaf(m210, a2, fmaf(m012, c2, m111 * ac)))));
-    const float gCz = fmaf(3.f * m003, c2, fmaf(2.f * m102, ac, fmaf(2.f * m012, bc, fmaf(m201, a2, fmaf(m021, b2, m111 * ab)))));
-    const float C3 = fmaf(gCz, c, fmaf(gCy, b, gCx * a));                 // 3 C(u)
+    float gCx = 0.f, gCy = 0.f, gCz = 0.f, C3;
+    if (WANT & 2) {  // the gradient is needed anyway: C = u.gradC / 3 (Euler)
+        gCx = fmaf(3.f * m300, a2, fmaf(2.f * m210, ab, fmaf(2.f * m201, ac, fmaf(m120, b2, fmaf(m102, c2, m111 * bc)))));
+        gCy = fmaf(3.f * m030, b2, fmaf(2.f * m120, ab, fmaf(2.f * m021, bc, fmaf(m210, a2, fmaf(m012, c2, m111 * ac)))));
+        gCz = fmaf(3.f * m003, c2, fmaf(2.f * m102, ac, fmaf(2.f * m012, bc, fmaf(m201, a2, fmaf(m021, b2, m111 * ab)))));
+        C3 = fmaf(gCz, c, fmaf(gCy, b, gCx * a));                         // 3 C(u)
+    } else {         // potential only: the cubic form directly
+        const float cx = fmaf(m201, c, fmaf(m210, b, m300 * a));
+        const float cy = fmaf(m021, c, fmaf(m120, a, m030 * b));
+        const float cz = fmaf(m012, b, fmaf(m102, a, m003 * c));
+        C3 = 3.f * fmaf(m111 * a, bc, fmaf(c2, cz, fmaf(b2, cy, a2 * cx)));
+    }
     const float wu3 = fmaf(r[20], c, fmaf(r[19], b, r[18] * a));          // 9 v.u
     float phi = 0.f;
     if (WANT & 1) {
@@ -538,13 +546,21 @@ __device__ __forceinline__ void m2p_fast45(const float* __restrict__ rec, float 
                     m031 = r[31], m013 = r[32], m220 = r[33], m202 = r[34], m022 = r[35], m211 = r[36], m121 = r[37],
                     m112 = r[38];
         const float a3 = a2 * a, b3 = b2 * b, c3p = c2 * c;
-        const float gQx = 4.f * m400 * a3 + 3.f * (m310 * a2 * b + m301 * a2 * c) + m130 * b3 + m103 * c3p +
-                          2.f * a * (m220 * b2 + m202 * c2 + m211 * bc) + bc * (m121 * b + m112 * c);
-        const float gQy = 4.f * m040 * b3 + 3.f * (m130 * a * b2 + m031 * b2 * c) + m310 * a3 + m013 * c3p +
-                          2.f * b * (m220 * a2 + m022 * c2 + m121 * ac) + ac * (m211 * a + m112 * c);
-        const float gQz = 4.f * m004 * c3p + 3.f * (m103 * a * c2 + m013 * b * c2) + m301 * a3 + m031 * b3 +
-                          2.f * c * (m202 * a2 + m022 * b2 + m112 * ab) + ab * (m211 * a + m121 * b);
-        const float Q4 = fmaf(gQz, c, fmaf(gQy, b, gQx * a));             // 4 Q(u)
+        float gQx = 0.f, gQy = 0.f, gQz = 0.f, Q4;
+        if ((WANT & 2) && ORDER == 5) {  // gradient needed: Q = u.gradQ / 4 (Euler)
+            gQx = 4.f * m400 * a3 + 3.f * (m310 * a2 * b + m301 * a2 * c) + m130 * b3 + m103 * c3p +
+                  2.f * a * (m220 * b2 + m202 * c2 + m211 * bc) + bc * (m121 * b + m112 * c);
+            gQy = 4.f * m040 * b3 + 3.f * (m130 * a * b2 + m031 * b2 * c) + m310 * a3 + m013 * c3p +
+                  2.f * b * (m220 * a2 + m022 * c2 + m121 * ac) + ac * (m211 * a + m112 * c);
+            gQz = 4.f * m004 * c3p + 3.f * (m103 * a * c2 + m013 * b * c2) + m301 * a3 + m031 * b3 +
+                  2.f * c * (m202 * a2 + m022 * b2 + m112 * ab) + ab * (m211 * a + m121 * b);
+            Q4 = fmaf(gQz, c, fmaf(gQy, b, gQx * a));                     // 4 Q(u)
+        } else {                          // potential only: the quartic form directly
+            const float q3 = fmaf(a3, fmaf(m301, c, fmaf(m310, b, m400 * a)),
+                                  fmaf(b3, fmaf(m031, c, fmaf(m130, a, m040 * b)), c3p * fmaf(m013, b, fmaf(m103, a, m004 * c))));
+            const float q2 = fmaf(a2, fmaf(m211, bc, fmaf(m202, c2, m220 * b2)), fmaf(b2, fmaf(m121, ac, m022 * c2), m112 * ab * c2));
+            Q4 = 4.f * (q3 + q2);
+        }
         const float Lxx = r[39], Lyy = r[40], Lzz = r[41], Lxy = r[42], Lxz = r[43], Lyz = r[44], L2 = r[45];
         const float gLx = fmaf(2.f * Lxx, a, fmaf(Lxy, b, Lxz * c));      // grad LapQ
         const float gLy = fmaf(2.f * Lyy, b, fmaf(Lxy, a, Lyz * c));
