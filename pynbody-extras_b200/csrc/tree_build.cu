@@ -303,13 +303,17 @@ struct PayloadArgs {
     const double* spos; const double* smass; const double* sh;
     double* nmass; double* ncom; double* hmax; double* moments; int order; int ncoef;
 };
-template <int ORDER>  // effective order: 0 (monopole storage, multipole_order <= 1), 2, 3, 4, 5
+// LEAVES = true : one launch over ALL nodes, leaves only (P2M has no dependencies): ids == nullptr, id = thread index.
+// LEAVES = false: one launch per level, deepest first, internal nodes only (M2M from the finished children).
+// Splitting the two keeps warps convergent: leaves are 86 % of the nodes and do completely different work.
+template <int ORDER, bool LEAVES>  // effective order: 0 (monopole storage, multipole_order <= 1), 2, 3, 4, 5
 __global__ void __launch_bounds__(128) payload_level(PayloadArgs a) {
     constexpr int NC = mp::stored_coeffs(ORDER);
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.count) return;
-    const int32_t id = a.ids[j];
+    const int32_t id = LEAVES ? (int32_t)j : a.ids[j];
     const int nc = a.nchild[id];
+    if (LEAVES != (nc == 0)) return;
     double mass = 0.0, cx = 0.0, cy = 0.0, cz = 0.0, hm = 0.0;
     if (nc == 0) {
         const uint32_t s0 = a.start[id], c = a.pcount[id];
@@ -645,21 +649,28 @@ void build_mass_payload(pnbx_tree_impl& t, cudaStream_t s, StageTimer& tm) {
     if (t.has_hmax) t.hmax.alloc((size_t)nn, s); else t.hmax.release();
     t.n_moments = mp::stored_coeffs(t.order);
     t.moments.alloc((size_t)nn * t.n_moments, s);
-    for (int d = (int)t.level_off.size() - 2; d >= 0; --d) {
-        PayloadArgs a;
+    PayloadArgs a;
+    a.start = t.node_start.p; a.pcount = t.node_count.p; a.nchild = t.node_nchild.p; a.first_subnode = t.first_subnode.p;
+    a.spos = t.spos.p; a.smass = t.has_mass ? t.smass.p : nullptr; a.sh = t.has_h ? t.sh.p : nullptr;
+    a.nmass = t.nmass.p; a.ncom = t.ncom.p; a.hmax = t.has_hmax ? t.hmax.p : nullptr; a.moments = t.moments.p;
+    a.order = t.order; a.ncoef = t.n_moments;
+    const int eff = t.order <= 1 ? 0 : t.order;
+    auto launch = [&](bool leaves) {
+#define PNBX_P(O)                                                                                            \
+    if (eff == O) {                                                                                          \
+        if (leaves) PNBX_LAUNCH((payload_level<O, true>), nblk(a.count, 128), 128, 0, s, a);                 \
+        else PNBX_LAUNCH((payload_level<O, false>), nblk(a.count, 128), 128, 0, s, a);                       \
+    }
+        PNBX_P(0) PNBX_P(2) PNBX_P(3) PNBX_P(4) PNBX_P(5)
+#undef PNBX_P
+    };
+    a.ids = nullptr;
+    a.count = nn;
+    launch(true);  // every leaf of every level at once
+    for (int d = (int)t.level_off.size() - 3; d >= 0; --d) {  // the deepest level holds leaves only
         a.ids = t.level_ids.p + t.level_off[d];
         a.count = t.level_off[d + 1] - t.level_off[d];
-        a.start = t.node_start.p; a.pcount = t.node_count.p; a.nchild = t.node_nchild.p; a.first_subnode = t.first_subnode.p;
-        a.spos = t.spos.p; a.smass = t.has_mass ? t.smass.p : nullptr; a.sh = t.has_h ? t.sh.p : nullptr;
-        a.nmass = t.nmass.p; a.ncom = t.ncom.p; a.hmax = t.has_hmax ? t.hmax.p : nullptr; a.moments = t.moments.p;
-        a.order = t.order; a.ncoef = t.n_moments;
-        switch (t.order <= 1 ? 0 : t.order) {
-            case 0: PNBX_LAUNCH(payload_level<0>, nblk(a.count, 128), 128, 0, s, a); break;
-            case 2: PNBX_LAUNCH(payload_level<2>, nblk(a.count, 128), 128, 0, s, a); break;
-            case 3: PNBX_LAUNCH(payload_level<3>, nblk(a.count, 128), 128, 0, s, a); break;
-            case 4: PNBX_LAUNCH(payload_level<4>, nblk(a.count, 128), 128, 0, s, a); break;
-            default: PNBX_LAUNCH(payload_level<5>, nblk(a.count, 128), 128, 0, s, a); break;
-        }
+        launch(false);
     }
     t.rec.alloc((size_t)nn, s);
     PNBX_LAUNCH(build_walk_records, nblk(nn), 256, 0, s, t.nmass.p, t.ncom.p, t.half.p, t.has_hmax ? t.hmax.p : nullptr,
