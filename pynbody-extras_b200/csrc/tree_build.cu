@@ -382,6 +382,84 @@ __global__ void __launch_bounds__(128) payload_level(PayloadArgs a) {
     for (int t = 0; t < NC; ++t) a.moments[(int64_t)id * NC + t] = mom[t];
 }
 
+
+// Internal nodes of one level, 8 lanes per node (lane l <-> child slot l): every lane loads its child's mass / COM /
+// hmax, all lanes replay the reference's sequential sums over the children in octant order (identical bits on every
+// lane, tree.rs:907-925, 953-961), each lane translates ITS child's moments to the node's COM (the expensive M2M, now
+// 8-way parallel), and the lanes then add the translated sets coefficient-parallel, again in octant order
+// (tree.rs:1046-1061) — same operations in the same order as a serial sweep, bit-equal results.
+template <int ORDER>
+__global__ void __launch_bounds__(mp::stored_coeffs(ORDER) > 35 ? 64 : 128) payload_internal(PayloadArgs a) {
+    constexpr int NC = mp::stored_coeffs(ORDER);
+    constexpr int GROUPS = NC > 35 ? 8 : 16;  // nodes per block
+    __shared__ double s_tr[GROUPS][8][NC];
+    const int lane8 = threadIdx.x & 7, g = threadIdx.x >> 3;
+    const int64_t j = (int64_t)blockIdx.x * GROUPS + g;
+    int32_t id = -1;
+    int nc = 0;
+    if (j < a.count) {
+        id = a.ids[j];
+        nc = a.nchild[id];
+    }
+    const bool node_ok = nc > 0;  // leaves were handled by payload_level<ORDER, true>
+    const int32_t c0 = node_ok ? a.first_subnode[id] : 0;
+    const bool have = node_ok && lane8 < nc;
+    const int32_t c = c0 + lane8;
+    double cm = 0.0, ccx = 0.0, ccy = 0.0, ccz = 0.0, chm = 0.0;
+    if (have) {
+        cm = a.nmass[c];
+        ccx = a.ncom[3 * (int64_t)c]; ccy = a.ncom[3 * (int64_t)c + 1]; ccz = a.ncom[3 * (int64_t)c + 2];
+        if (a.hmax) chm = a.hmax[c];
+    }
+    double mass = 0.0, cx = 0.0, cy = 0.0, cz = 0.0, hm = 0.0;
+    unsigned nzmask = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double mk = __shfl_sync(0xffffffffu, cm, k, 8);
+        const double xk = __shfl_sync(0xffffffffu, ccx, k, 8), yk = __shfl_sync(0xffffffffu, ccy, k, 8),
+                     zk = __shfl_sync(0xffffffffu, ccz, k, 8), hk = __shfl_sync(0xffffffffu, chm, k, 8);
+        if (k < nc) {
+            hm = fmax(hm, hk);
+            if (mk != 0.0) {
+                nzmask |= 1u << k;
+                mass = __dadd_rn(mass, mk);
+                cx = __dadd_rn(cx, __dmul_rn(xk, mk));
+                cy = __dadd_rn(cy, __dmul_rn(yk, mk));
+                cz = __dadd_rn(cz, __dmul_rn(zk, mk));
+            }
+        }
+    }
+    if (mass > 0.0) {
+        cx = __ddiv_rn(cx, mass);
+        cy = __ddiv_rn(cy, mass);
+        cz = __ddiv_rn(cz, mass);
+    }
+    if (node_ok && lane8 == 0) {
+        a.nmass[id] = mass;
+        a.ncom[3 * (int64_t)id] = cx; a.ncom[3 * (int64_t)id + 1] = cy; a.ncom[3 * (int64_t)id + 2] = cz;
+        if (a.hmax) a.hmax[id] = hm;
+    }
+    if (have && cm != 0.0 && mass != 0.0) {
+        double tr[NC];
+#pragma unroll
+        for (int t = 0; t < NC; ++t) tr[t] = 0.0;
+        const double shift[3] = {__dsub_rn(cx, ccx), __dsub_rn(cy, ccy), __dsub_rn(cz, ccz)};
+        mp::m2m_accumulate_ct<ORDER, NC>(tr, a.moments + (int64_t)c * NC, shift);
+#pragma unroll
+        for (int t = 0; t < NC; ++t) s_tr[g][lane8][t] = tr[t];
+    }
+    __syncwarp();
+    if (node_ok) {
+        for (int t = lane8; t < NC; t += 8) {
+            double acc = 0.0;
+            if (mass != 0.0)
+                for (int k = 0; k < nc; ++k)
+                    if (nzmask & (1u << k)) acc = __dadd_rn(acc, s_tr[g][k][t]);
+            a.moments[(int64_t)id * NC + t] = acc;
+        }
+    }
+}
+
 __global__ void build_walk_records(const double* __restrict__ nmass, const double* __restrict__ ncom,
                                    const double* __restrict__ half, const double* __restrict__ hmax, double csep,
                                    const uint8_t* __restrict__ nchild, const uint32_t* __restrict__ start,
@@ -659,7 +737,8 @@ void build_mass_payload(pnbx_tree_impl& t, cudaStream_t s, StageTimer& tm) {
 #define PNBX_P(O)                                                                                            \
     if (eff == O) {                                                                                          \
         if (leaves) PNBX_LAUNCH((payload_level<O, true>), nblk(a.count, 128), 128, 0, s, a);                 \
-        else PNBX_LAUNCH((payload_level<O, false>), nblk(a.count, 128), 128, 0, s, a);                       \
+        else PNBX_LAUNCH((payload_internal<O>), nblk(a.count, mp::stored_coeffs(O) > 35 ? 8 : 16),            \
+                         mp::stored_coeffs(O) > 35 ? 64 : 128, 0, s, a);                                     \
     }
         PNBX_P(0) PNBX_P(2) PNBX_P(3) PNBX_P(4) PNBX_P(5)
 #undef PNBX_P
