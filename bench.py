@@ -233,9 +233,15 @@ def tree_section(args, rank, world, local, dev, barrier, peak_tf):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(reps):
+            ta = time.perf_counter()
             g = Gravity(pos_h, mass_h, softening=h_h, kernel=KernelKind.Spline)
+            _ = g.tree
+            tb = time.perf_counter()
             out = g.tree_potentials(theta=theta)
+            tc = time.perf_counter()
             del g
+            print(f"[bench] tree e2e: construct {1e3 * (tb - ta):.1f} ms, potentials {1e3 * (tc - tb):.1f} ms, "
+                  f"free {1e3 * (time.perf_counter() - tc):.1f} ms", file=sys.stderr)
         dt = (time.perf_counter() - t0) / reps
         res["e2e"] = {"value": n / dt, "unit": "particles/s", "ms_per_step": dt * 1e3,
                       "h2d_bytes_per_step": int(pos.nbytes + mass.nbytes + h.nbytes), "d2h_bytes_per_step": int(out.nbytes),
