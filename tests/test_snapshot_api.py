@@ -72,3 +72,22 @@ def test_units_and_methods(fake_pynbody):
     # softening without a kernel is an error from the backend
     with pytest.raises(ValueError, match="softenings require an explicit kernel"):
         calculate_potential(sim, softening=0.01, method="direct")
+
+
+@pytest.mark.gpu
+def test_property_nodes_use_the_active_view(fake_pynbody):
+    # a filtered / shifted view reaches gravity only as its pos / mass arrays: the node must evaluate
+    # exactly what calculate_potential gives for that view
+    from pynbodyext.gravity import calculate_potential
+    from pynbodyext.gravity.properties import GravityAcceleration, GravityPotential
+    sim, pos, m = make_sim(fake_pynbody, n=4000, seed=9)
+    keep = (pos ** 2).sum(1) < 4.0  # "Sphere(2 kpc)" filter
+    view = fake_pynbody.snapshot.SimSnap(pos=fake_pynbody.array.SimArray(pos[keep] - pos[keep].mean(0), "kpc"),
+                                         mass=fake_pynbody.array.SimArray(m[keep], "Msol"))
+    node = GravityPotential(softening=0.05, kernel=1, theta=0.6)
+    got = node(view)
+    ref = calculate_potential(view, softening=0.05, kernel=1, theta=0.6)
+    assert np.array_equal(np.asarray(got), np.asarray(ref)) and got.sim is view
+    acc = GravityAcceleration(method="direct")(view)
+    assert acc.shape == (int(keep.sum()), 3) and np.isfinite(np.asarray(acc)).all()
+    assert node.instance_signature() == GravityPotential(softening=0.05, kernel=1, theta=0.6).instance_signature()
