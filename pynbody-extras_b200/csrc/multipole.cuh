@@ -39,17 +39,6 @@ __device__ constexpr Lmn kLmn[NCOEF] = {
     {1, 4, 0}, {1, 0, 4}, {0, 4, 1}, {0, 1, 4}, {3, 2, 0}, {3, 0, 2}, {2, 3, 0}, {2, 0, 3}, {0, 3, 2}, {0, 2, 3},
     {2, 2, 1}, {2, 1, 2}, {1, 2, 2}, {3, 1, 1}, {1, 3, 1}, {1, 1, 3}};
 
-// (l,m,n) -> field index; only l+m+n <= 5 is ever looked up
-__device__ inline int lmn_index(int l, int m, int n) {
-    // small perfect hash over the 56 valid triples: search the order block (at most 21 entries)
-    const int o = l + m + n;
-    const int lo = o == 0 ? 0 : o == 1 ? 1 : o == 2 ? 4 : o == 3 ? 10 : o == 4 ? 20 : 35;
-    const int hi = o == 0 ? 1 : o == 1 ? 4 : o == 2 ? 10 : o == 3 ? 20 : o == 4 ? 35 : 56;
-    for (int i = lo; i < hi; ++i)
-        if (kLmn[i].l == l && kLmn[i].m == m) return i;  // n is implied by the order block
-    return -1;
-}
-
 // ---- P2M ---------------------------------------------------------------------------------------
 // Each coefficient adds  ((c * mass) * f1) * f2 ...  with the factor sequence the reference
 // writes (e.g. m120 += 0.5*mass*y*y*x). A factor is a coordinate (power 1) or a powi() value.
@@ -87,73 +76,12 @@ __device__ constexpr P2MTerm kP2M[NCOEF] = {
 #undef PY
 #undef PZ
 
-// integer power by square-and-multiply, the operation order of compiler-rt's __powidf2 (f64::powi)
-__device__ inline double powi_rn(double a, int b) {
-    double r = 1.0;
-    for (;;) {
-        if (b & 1) r = __dmul_rn(r, a);
-        b >>= 1;
-        if (b == 0) break;
-        a = __dmul_rn(a, a);
-    }
-    return r;
-}
-
-// accumulate one particle (offset x,y,z from the expansion centre) into mom[0..ncoef)
-__device__ inline void p2m_accumulate(double* mom, int ncoef, double mass, double x, double y, double z) {
-    double pw[3][6];
-    const double v[3] = {x, y, z};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        pw[a][1] = v[a];
-#pragma unroll
-        for (int p = 2; p <= 5; ++p) pw[a][p] = powi_rn(v[a], p);
-    }
-    mom[0] = __dadd_rn(mom[0], mass);
-    for (int i = 1; i < ncoef; ++i) {
-        double t = __dmul_rn(kP2M[i].c, mass);
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const int tok = kP2M[i].tok[k];
-            if (tok == 0) break;
-            t = __dmul_rn(t, pw[tok >> 3][tok & 7]);
-        }
-        mom[i] = __dadd_rn(mom[i], t);
-    }
-}
-
-// ---- M2M ---------------------------------------------------------------------------------------
-// out[lmn] = sum_{i<=l, j<=m, k<=n} (-1)^(d) shift^d / d! * child[ijk],  d = (l-i, m-j, n-k),
-// accumulated in the reference's loop order; `acc` += out (add_assign, multipole.rs:173-230).
-__device__ inline void m2m_accumulate(double* acc, const double* child, int order, int ncoef, const double shift[3]) {
-    const double fact[6] = {1.0, 1.0, 2.0, 6.0, 24.0, 120.0};
-    double spw[3][6];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        spw[a][0] = 1.0;
-#pragma unroll
-        for (int p = 1; p <= 5; ++p) spw[a][p] = powi_rn(shift[a], p);
-    }
-    for (int t = 0; t < ncoef; ++t) {
-        const int l = kLmn[t].l, m = kLmn[t].m, n = kLmn[t].n;
-        if (l + m + n > order) continue;
-        double sum = 0.0;
-        for (int i = 0; i <= l; ++i)
-            for (int j = 0; j <= m; ++j)
-                for (int k = 0; k <= n; ++k) {
-                    const double base = child[lmn_index(i, j, k)];
-                    if (base == 0.0) continue;
-                    const int dl = l - i, dm = m - j, dn = n - k;
-                    double pw = (dl + dm + dn == 0) ? 1.0 : __dmul_rn(__dmul_rn(spw[0][dl], spw[1][dm]), spw[2][dn]);
-                    const double sign = ((dl + dm + dn) & 1) ? -1.0 : 1.0;
-                    const double coeff = __ddiv_rn(__dmul_rn(sign, pw), __dmul_rn(__dmul_rn(fact[dl], fact[dm]), fact[dn]));
-                    sum = __dadd_rn(sum, __dmul_rn(coeff, base));
-                }
-        acc[t] = __dadd_rn(acc[t], sum);
-    }
-}
-
-// Compile-time-order variants: with ORDER a template parameter every loop below unrolls, the tables
+// ---- P2M / M2M, order known at compile time -------------------------------------------------------
+// f64::powi is compiler-rt's __powidf2 (square-and-multiply): x^2 = x*x, x^3 = x*(x*x), x^4 = (x*x)*(x*x),
+// x^5 = x*((x*x)*(x*x)) — the products below are written in exactly that order.
+// M2M: out[lmn] = sum_{i<=l, j<=m, k<=n} (-1)^|d| shift^d / d! * child[ijk], d = (l-i, m-j, n-k), accumulated in the
+// reference's loop order (multipole.rs:1544-1592); the caller's `acc` += out (add_assign, multipole.rs:173-230).
+// With ORDER a template parameter every loop below unrolls, the tables
 // fold to constants, moments live in registers and the only true divisions left are by 6, 12, 24, ...
 // (division by 1, 2, 4 is exact, so it is issued as a multiplication). Same operation order, same bits.
 template <int NC>

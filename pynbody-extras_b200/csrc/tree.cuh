@@ -43,7 +43,6 @@ struct pnbx_tree_impl {
     // per particle
     DevBuf<uint64_t> key_hi, key_lo;   // original order
     DevBuf<uint32_t> perm;             // sorted position -> original index (ascending inside a leaf)
-    DevBuf<uint32_t> inv_perm;         // original index -> sorted position
     // sorted copies used by payload builds and the walk
     DevBuf<double> spos;               // (n,3) float64
     DevBuf<double> smass, sh;          // float64 (smass only if has_mass, sh only if has_h)
@@ -62,7 +61,6 @@ struct pnbx_tree_impl {
     // level_ids[level_off[d] .. level_off[d+1])
     DevBuf<int32_t> level_ids;
     std::vector<int64_t> level_off;
-    DevBuf<int32_t> parent;            // reference id of the parent (-1 for the root)
 
     // payloads
     DevBuf<double> nmass, ncom, hmax;  // (nn), (nn,3), (nn)

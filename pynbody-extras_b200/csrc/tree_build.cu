@@ -218,7 +218,7 @@ __global__ void links_level(const int32_t* __restrict__ parent, const uint8_t* _
 }
 struct FinalArrays {
     double* center; double* half; uint8_t* depth; uint32_t* start; uint32_t* count; int32_t* first_subnode;
-    int32_t* next_branch; uint64_t* path_hi; uint64_t* path_lo; int32_t* parent; uint8_t* nchild; int32_t* level_ids;
+    int32_t* next_branch; uint64_t* path_hi; uint64_t* path_lo; uint8_t* nchild; int32_t* level_ids;
 };
 __global__ void scatter_nodes(const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
                               const int32_t* __restrict__ parent, const uint8_t* __restrict__ depth,
@@ -239,7 +239,6 @@ __global__ void scatter_nodes(const uint32_t* __restrict__ start, const uint32_t
     f.next_branch[r] = nb_bfs[i];
     f.path_hi[r] = phi[i];
     f.path_lo[r] = plo[i];
-    f.parent[r] = i == 0 ? -1 : ref[parent[i]];
     f.nchild[r] = nchild[i];
     f.level_ids[i] = r;  // BFS order is level order
 }
@@ -256,11 +255,6 @@ __global__ void leaf_ordinal_to_particles(const uint32_t* __restrict__ ord_sorte
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s < n) ord_orig[perm[s]] = ord_sorted[s];
 }
-__global__ void invert_perm(const uint32_t* __restrict__ perm, int64_t n, uint32_t* __restrict__ inv) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n) inv[perm[s]] = (uint32_t)s;
-}
-
 // ---- sorted copies
 __global__ void gather_sources(const double* __restrict__ pos, const double* __restrict__ mass,
                                const uint32_t* __restrict__ perm, int64_t n, double* __restrict__ spos,
@@ -303,48 +297,30 @@ struct PayloadArgs {
     const double* spos; const double* smass; const double* sh;
     double* nmass; double* ncom; double* hmax; double* moments; int order; int ncoef;
 };
-// LEAVES = true : one launch over ALL nodes, leaves only (P2M has no dependencies): ids == nullptr, id = thread index.
-// LEAVES = false: one launch per level, deepest first, internal nodes only (M2M from the finished children).
-// Splitting the two keeps warps convergent: leaves are 86 % of the nodes and do completely different work.
-template <int ORDER, bool LEAVES>  // effective order: 0 (monopole storage, multipole_order <= 1), 2, 3, 4, 5
-__global__ void __launch_bounds__(128) payload_level(PayloadArgs a) {
+// Leaves: one launch over ALL nodes (P2M has no dependencies), one thread per node, internal nodes return at once.
+// Mass / COM / hmax in leaf-list order (tree.rs:881-905, 947-952), then P2M about the COM (tree.rs:1030-1042).
+template <int ORDER>  // effective order: 0 (monopole storage, multipole_order <= 1), 2, 3, 4, 5
+__global__ void __launch_bounds__(128) payload_leaves(PayloadArgs a) {
     constexpr int NC = mp::stored_coeffs(ORDER);
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= a.count) return;
-    const int32_t id = LEAVES ? (int32_t)j : a.ids[j];
-    const int nc = a.nchild[id];
-    if (LEAVES != (nc == 0)) return;
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= a.count || a.nchild[id] != 0) return;
     double mass = 0.0, cx = 0.0, cy = 0.0, cz = 0.0, hm = 0.0;
-    if (nc == 0) {
-        const uint32_t s0 = a.start[id], c = a.pcount[id];
-        for (uint32_t s = s0; s < s0 + c; ++s) {
-            const double px = a.spos[3 * (int64_t)s], py = a.spos[3 * (int64_t)s + 1], pz = a.spos[3 * (int64_t)s + 2];
-            if (a.smass) {
-                const double m = a.smass[s];
-                mass = __dadd_rn(mass, m);
-                cx = __dadd_rn(cx, __dmul_rn(px, m));
-                cy = __dadd_rn(cy, __dmul_rn(py, m));
-                cz = __dadd_rn(cz, __dmul_rn(pz, m));
-            } else {
-                mass = __dadd_rn(mass, 1.0);
-                cx = __dadd_rn(cx, px);
-                cy = __dadd_rn(cy, py);
-                cz = __dadd_rn(cz, pz);
-            }
-            if (a.hmax) hm = fmax(hm, fmax(a.sh[s], 0.0));
+    const uint32_t s0 = a.start[id], c = a.pcount[id];
+    for (uint32_t s = s0; s < s0 + c; ++s) {
+        const double px = a.spos[3 * (int64_t)s], py = a.spos[3 * (int64_t)s + 1], pz = a.spos[3 * (int64_t)s + 2];
+        if (a.smass) {
+            const double m = a.smass[s];
+            mass = __dadd_rn(mass, m);
+            cx = __dadd_rn(cx, __dmul_rn(px, m));
+            cy = __dadd_rn(cy, __dmul_rn(py, m));
+            cz = __dadd_rn(cz, __dmul_rn(pz, m));
+        } else {
+            mass = __dadd_rn(mass, 1.0);
+            cx = __dadd_rn(cx, px);
+            cy = __dadd_rn(cy, py);
+            cz = __dadd_rn(cz, pz);
         }
-    } else {
-        const int32_t c0 = a.first_subnode[id];
-        for (int k = 0; k < nc; ++k) {
-            const int32_t c = c0 + k;
-            if (a.hmax) hm = fmax(hm, a.hmax[c]);
-            const double cm = a.nmass[c];
-            if (cm == 0.0) continue;
-            mass = __dadd_rn(mass, cm);
-            cx = __dadd_rn(cx, __dmul_rn(a.ncom[3 * (int64_t)c], cm));
-            cy = __dadd_rn(cy, __dmul_rn(a.ncom[3 * (int64_t)c + 1], cm));
-            cz = __dadd_rn(cz, __dmul_rn(a.ncom[3 * (int64_t)c + 2], cm));
-        }
+        if (a.hmax) hm = fmax(hm, fmax(a.sh[s], 0.0));
     }
     if (mass > 0.0) {
         cx = __ddiv_rn(cx, mass);
@@ -352,36 +328,21 @@ __global__ void __launch_bounds__(128) payload_level(PayloadArgs a) {
         cz = __ddiv_rn(cz, mass);
     }
     a.nmass[id] = mass;
-    a.ncom[3 * (int64_t)id] = cx; a.ncom[3 * (int64_t)id + 1] = cy; a.ncom[3 * (int64_t)id + 2] = cz;
+    a.ncom[3 * id] = cx; a.ncom[3 * id + 1] = cy; a.ncom[3 * id + 2] = cz;
     if (a.hmax) a.hmax[id] = hm;
-
-    // multipoles about the node's centre of mass
     double mom[NC];
 #pragma unroll
     for (int t = 0; t < NC; ++t) mom[t] = 0.0;
     if (mass != 0.0) {
-        if (nc == 0) {
-            const uint32_t s0 = a.start[id], c = a.pcount[id];
-            for (uint32_t s = s0; s < s0 + c; ++s) {
-                const double m = a.smass ? a.smass[s] : 1.0;
-                mp::p2m_accumulate_ct<NC>(mom, m, __dsub_rn(a.spos[3 * (int64_t)s], cx),
-                                          __dsub_rn(a.spos[3 * (int64_t)s + 1], cy), __dsub_rn(a.spos[3 * (int64_t)s + 2], cz));
-            }
-        } else {
-            const int32_t c0 = a.first_subnode[id];
-            for (int k = 0; k < nc; ++k) {
-                const int32_t c = c0 + k;
-                if (a.nmass[c] == 0.0) continue;
-                const double shift[3] = {__dsub_rn(cx, a.ncom[3 * (int64_t)c]), __dsub_rn(cy, a.ncom[3 * (int64_t)c + 1]),
-                                         __dsub_rn(cz, a.ncom[3 * (int64_t)c + 2])};
-                mp::m2m_accumulate_ct<ORDER, NC>(mom, a.moments + (int64_t)c * NC, shift);
-            }
+        for (uint32_t s = s0; s < s0 + c; ++s) {
+            const double m = a.smass ? a.smass[s] : 1.0;
+            mp::p2m_accumulate_ct<NC>(mom, m, __dsub_rn(a.spos[3 * (int64_t)s], cx), __dsub_rn(a.spos[3 * (int64_t)s + 1], cy),
+                                      __dsub_rn(a.spos[3 * (int64_t)s + 2], cz));
         }
     }
 #pragma unroll
-    for (int t = 0; t < NC; ++t) a.moments[(int64_t)id * NC + t] = mom[t];
+    for (int t = 0; t < NC; ++t) a.moments[id * NC + t] = mom[t];
 }
-
 
 // Internal nodes of one level, 8 lanes per node (lane l <-> child slot l): every lane loads its child's mass / COM /
 // hmax, all lanes replay the reference's sequential sums over the children in octant order (identical bits on every
@@ -401,7 +362,7 @@ __global__ void __launch_bounds__(mp::stored_coeffs(ORDER) > 35 ? 64 : 128) payl
         id = a.ids[j];
         nc = a.nchild[id];
     }
-    const bool node_ok = nc > 0;  // leaves were handled by payload_level<ORDER, true>
+    const bool node_ok = nc > 0;  // leaves were handled by payload_leaves<ORDER>
     const int32_t c0 = node_ok ? a.first_subnode[id] : 0;
     const bool have = node_ok && lane8 < nc;
     const int32_t c = c0 + lane8;
@@ -671,10 +632,10 @@ bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const DevBuf<double>& roo
     t.node_start.alloc((size_t)nn, s); t.node_count.alloc((size_t)nn, s);
     t.first_subnode.alloc((size_t)nn, s); t.next_branch.alloc((size_t)nn, s);
     t.path_hi.alloc((size_t)nn, s); t.path_lo.alloc((size_t)nn, s);
-    t.parent.alloc((size_t)nn, s); t.level_ids.alloc((size_t)nn, s);
+    t.level_ids.alloc((size_t)nn, s);
     DevBuf<uint8_t> nchild_ref((size_t)nn, s);
     FinalArrays f{t.center.p, t.half.p, t.node_depth.p, t.node_start.p, t.node_count.p, t.first_subnode.p,
-                  t.next_branch.p, t.path_hi.p, t.path_lo.p, t.parent.p, nchild_ref.p, t.level_ids.p};
+                  t.next_branch.p, t.path_hi.p, t.path_lo.p, nchild_ref.p, t.level_ids.p};
     PNBX_LAUNCH(scatter_nodes, nblk(nn), 256, 0, s, b.start.p, b.count.p, b.parent.p, b.depth.p, b.nchild.p, b.center.p,
                 b.half.p, b.path_hi.p, b.path_lo.p, ref.p, first_child_ref.p, nb_bfs.p, nn, f);
     t.n_leaves = nn - ni;
@@ -693,8 +654,6 @@ bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const DevBuf<double>& roo
         sort_pairs<uint32_t>(lord_orig.p, lord_out.p, iota.p, perm2.p, n, bits_for((uint64_t)t.n_leaves + 1), s);
         t.perm = std::move(perm2);
     }
-    t.inv_perm.alloc((size_t)std::max<int64_t>(n, 1), s);
-    if (n > 0) PNBX_LAUNCH(invert_perm, nblk(n), 256, 0, s, t.perm.p, n, t.inv_perm.p);
     tm.end();
     PNBX_CUDA(cudaGetLastError());
     t.node_nchild = std::move(nchild_ref);  // child counts in reference numbering, for the payload sweeps
@@ -736,7 +695,7 @@ void build_mass_payload(pnbx_tree_impl& t, cudaStream_t s, StageTimer& tm) {
     auto launch = [&](bool leaves) {
 #define PNBX_P(O)                                                                                            \
     if (eff == O) {                                                                                          \
-        if (leaves) PNBX_LAUNCH((payload_level<O, true>), nblk(a.count, 128), 128, 0, s, a);                 \
+        if (leaves) PNBX_LAUNCH((payload_leaves<O>), nblk(a.count, 128), 128, 0, s, a);                      \
         else PNBX_LAUNCH((payload_internal<O>), nblk(a.count, mp::stored_coeffs(O) > 35 ? 8 : 16),            \
                          mp::stored_coeffs(O) > 35 ? 64 : 128, 0, s, a);                                     \
     }
