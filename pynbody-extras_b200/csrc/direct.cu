@@ -171,11 +171,11 @@ template <int WANT, class T>
 __device__ __forceinline__ void spline_outside(T xi, T yi, T zi, T hi, const Vec4<T>& s, T hj, bool& inside, T& ax,
                                                T& ay, T& az, T& pot) {
     const T dx = s.x - xi, dy = s.y - yi, dz = s.z - zi;
-    const T h = tmax(hi, hj);
+    const T h = tmax(hi, hj);  // both clamped at 0 when packed, so "h > 0" is implied by r2 < h*h (r2 >= tiny > 0)
     T r2 = fma(dx, dx, tiny<T>());
     r2 = fma(dy, dy, r2);
     r2 = fma(dz, dz, r2);
-    const bool in = h > T(0) && r2 < h * h;  // kernel.rs:46-54, 72-80
+    const bool in = fma(-h, h, r2) < T(0);  // r < h: kernel.rs:46-54, 72-80
     inside |= in;
     const T m = in ? T(0) : s.w;
     const T rinv = rsqrt_fast(r2);
@@ -196,7 +196,7 @@ __device__ __forceinline__ void spline_inside(T xi, T yi, T zi, T hi, const Vec4
     T r2 = fma(dx, dx, tiny<T>());
     r2 = fma(dy, dy, r2);
     r2 = fma(dz, dz, r2);
-    if (!(h > T(0) && r2 < h * h)) return;
+    if (!(fma(-h, h, r2) < T(0))) return;  // the same predicate as pass 1, bit for bit
     const T rinv = rsqrt_fast(r2);
     const T hinv = T(1) / h;
     const T u = (r2 * rinv) * hinv;
@@ -559,11 +559,15 @@ __global__ void pack_points(const double* __restrict__ pos, const double* __rest
     v.w = mass ? (T)mass[i] : w_default;
     out[i] = v;
 }
+// clamp0: the cubic spline treats h <= 0 as Newtonian (kernel.rs:46-48, 72-74), and max(h_i, h_j) <= 0 iff both are,
+// so clamping every h at 0 up front leaves all spline results unchanged and saves a compare per pair.
 template <class T>
-__global__ void pack_scalar(const double* __restrict__ in, int64_t n, int64_t n_padded, T* __restrict__ out) {
+__global__ void pack_scalar(const double* __restrict__ in, int64_t n, int64_t n_padded, bool clamp0, T* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_padded) return;
-    out[i] = i < n ? (T)in[i] : T(0);
+    double v = i < n ? in[i] : 0.0;
+    if (clamp0) v = fmax(v, 0.0);
+    out[i] = (T)v;
 }
 // min / max of the softening array, to detect the (common) constant-softening case.
 __global__ void minmax_scalar_blocks(const double* __restrict__ in, int64_t n, double* __restrict__ part) {
@@ -691,7 +695,7 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     if (pair_h) {
         int64_t np = ceil_div(n, 4) * 4 + 4;  // padded to 16 B granules for the bulk copy
         srch.alloc((size_t)np, s);
-        PNBX_LAUNCH(pack_scalar<T>, (unsigned)ceil_div(np, 256), 256, 0, s, d_h, n, np, srch.get());
+        PNBX_LAUNCH(pack_scalar<T>, (unsigned)ceil_div(np, 256), 256, 0, s, d_h, n, np, soft == SOFT_SPLINE, srch.get());
     }
     DevBuf<Vec4<T>> tgt4;
     const Vec4<T>* tgt_ptr;
