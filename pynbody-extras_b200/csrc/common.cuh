@@ -113,6 +113,10 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// staging.cu: host<->device copies; large PAGEABLE host arrays are staged through pinned buffers by a few host threads
+void copy_h2d(void* dev, const void* host, size_t bytes, const Exec& ex);
+void copy_d2h(void* host, const void* dev, size_t bytes, const Exec& ex);
+
 // Input array that may live on the host (copied in, like gravity.rs:154-180) or on the device.
 template <class T>
 struct InArray {
@@ -122,7 +126,7 @@ struct InArray {
         if (!src || count == 0) { d = nullptr; return; }
         if (ex.device_ptrs) { d = src; return; }
         owned.alloc(count, ex.stream);
-        PNBX_CUDA(cudaMemcpyAsync(owned.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ex.stream));
+        copy_h2d(owned.p, src, count * sizeof(T), ex);
         d = owned.p;
     }
 };
@@ -143,7 +147,7 @@ struct OutArray {
         host = dst;
     }
     void finish(const Exec& ex) {
-        if (host && n) PNBX_CUDA(cudaMemcpyAsync(host, d, n * sizeof(T), cudaMemcpyDeviceToHost, ex.stream));
+        if (host && n) copy_d2h(host, d, n * sizeof(T), ex);
     }
 };
 

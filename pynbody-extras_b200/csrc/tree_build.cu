@@ -764,9 +764,9 @@ extern "C" int pnbx_tree_create(pnbx_tree** out, const double* pos, const double
         tm.begin("octree.copy_in");
         auto copy_in = [&](DevBuf<double>& dst, const double* src, size_t cnt) {
             dst.alloc(std::max<size_t>(cnt, 1), s);
-            if (cnt)
-                PNBX_CUDA(cudaMemcpyAsync(dst.p, src, cnt * sizeof(double),
-                                          ex.device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+            if (!cnt) return;
+            if (ex.device_ptrs) PNBX_CUDA(cudaMemcpyAsync(dst.p, src, cnt * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            else copy_h2d(dst.p, src, cnt * sizeof(double), ex);
         };
         copy_in(t->pos, pos, (size_t)3 * n);
         if (mass) copy_in(t->mass, mass, (size_t)n);
