@@ -31,7 +31,7 @@ Lane g_lanes[MAX_THREADS];
 int staging_threads() {
     static const int n = [] {
         const char* e = getenv("PNBX_STAGING_THREADS");
-        int v = e ? atoi(e) : 4;
+        int v = e ? atoi(e) : 8;  // measured: 4 threads ~25 GB/s, 8 threads ~50 GB/s (pinned-memory speed)
         unsigned hw = std::thread::hardware_concurrency();
         if (hw && (unsigned)v > hw) v = (int)hw;
         return std::max(0, std::min(v, MAX_THREADS));
