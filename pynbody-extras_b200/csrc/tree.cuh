@@ -21,8 +21,15 @@ struct alignas(64) NodeRec {
     int32_t next_branch;  // tree.rs:736-776; -1 = end of walk
     int32_t first;        // internal: first_subnode; leaf: first particle (sorted order)
     int32_t kind;         // >= 0: leaf with `kind` particles; -1: internal; -2: zero mass (skip subtree)
-    int32_t pad;
+    int32_t nleaf;        // leaf records only: number of reference leaves this record stands for (see below)
 };
+// Leaf runs. Every lane that opens a node visits ALL of its children, and leaves are always summed directly, so a
+// maximal run of consecutive non-zero-mass sibling leaves (consecutive reference ids, contiguous sorted particles) is
+// visited by the same lanes one leaf after the other. The walk records merge such a run into the record of its first
+// leaf: `first`/`kind` cover the particles of the whole run, `next_branch` is the last leaf's, `nleaf` the number of
+// leaves, and `com` is the run's origin for the fp32 sources (mean of the leaf COMs). The other leaves of the run
+// keep their single-leaf records but are unreachable: nothing links to them (links and resume points only ever target
+// a first child or the sibling after an internal node). The interaction list of every target is unchanged.
 static_assert(sizeof(NodeRec) == 64, "NodeRec must be one 64-byte record");
 
 struct pnbx_tree_impl {
@@ -46,8 +53,8 @@ struct pnbx_tree_impl {
     // sorted copies used by payload builds and the walk
     DevBuf<double> spos;               // (n,3) float64
     DevBuf<double> smass, sh;          // float64 (smass only if has_mass, sh only if has_h)
-    DevBuf<float4> src32;              // (x, y, z, m) float32, relative to the COM of the particle's leaf
-    DevBuf<float> sh32;
+    DevBuf<float4> src32;              // (x, y, z, m) float32, relative to the origin of the particle's leaf run
+    DevBuf<float> sh32;                // max(h,0)^2 in float32, sorted order
 
     // nodes, reference numbering
     int64_t nn = 0, n_leaves = 0;

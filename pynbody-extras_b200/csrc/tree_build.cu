@@ -266,26 +266,14 @@ __global__ void gather_sources(const double* __restrict__ pos, const double* __r
     spos[3 * s] = x; spos[3 * s + 1] = y; spos[3 * s + 2] = z;
     if (smass) smass[s] = mass[i];
 }
-// fp32 walk sources: every leaf's particles relative to that leaf's centre of mass (float64 subtraction,
-// then the cast), so close pairs keep their separation wherever the leaf sits in the box.
-__global__ void leaf_local_sources(const uint8_t* __restrict__ nchild, const uint32_t* __restrict__ start,
-                                   const uint32_t* __restrict__ count, const double* __restrict__ ncom,
-                                   const double* __restrict__ spos, const double* __restrict__ smass, int64_t nn,
-                                   float4* __restrict__ src32) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nn || nchild[i] != 0) return;
-    const double cx = ncom[3 * i], cy = ncom[3 * i + 1], cz = ncom[3 * i + 2];
-    for (uint32_t s = start[i]; s < start[i] + count[i]; ++s)
-        src32[s] = make_float4((float)(spos[3 * (int64_t)s] - cx), (float)(spos[3 * (int64_t)s + 1] - cy),
-                               (float)(spos[3 * (int64_t)s + 2] - cz), smass ? (float)smass[s] : 1.0f);
-}
 __global__ void gather_soft(const double* __restrict__ h, const uint32_t* __restrict__ perm, int64_t n,
                             double* __restrict__ sh, float* __restrict__ sh32) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const double v = h[perm[s]];
     sh[s] = v;
-    sh32[s] = (float)v;
+    const float hc = (float)fmax(v, 0.0);
+    sh32[s] = hc * hc;  // the fp32 walk compares squares: max(h_s,0)^2 (tree_walk.cu leaf_pass1_f32)
 }
 
 // ------------------------------------------------------------------------------------------ K6
@@ -441,8 +429,55 @@ __global__ void build_walk_records(const double* __restrict__ nmass, const doubl
     if (nmass[i] == 0.0) { r.kind = -2; r.first = -1; }          // tree.rs:1087-1090
     else if (nchild[i] == 0) { r.kind = (int32_t)count[i]; r.first = (int32_t)start[i]; }
     else { r.kind = -1; r.first = first_subnode[i]; }
-    r.pad = 0;
+    r.nleaf = 1;
     rec[i] = r;
+}
+// Leaf runs (tree.cuh) + the fp32 walk sources. One thread per sibling block (= per internal node, plus the root when
+// the root itself is a leaf): merges every maximal run of consecutive non-zero-mass leaf children into the record of
+// the run's first leaf and writes the run's particles relative to the run's origin (float64 subtraction, then the
+// cast: close pairs keep their separation wherever the run sits in the box).
+__global__ void merge_leaf_runs(const uint8_t* __restrict__ nchild, const int32_t* __restrict__ first_subnode,
+                                const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
+                                const int32_t* __restrict__ next_branch, const double* __restrict__ nmass,
+                                const double* __restrict__ ncom, const double* __restrict__ spos,
+                                const double* __restrict__ smass, int64_t nn, NodeRec* __restrict__ rec,
+                                float4* __restrict__ src32) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nn) return;
+    int64_t c0, c1;  // the sibling block [c0, c1)
+    if (nchild[p] != 0) { c0 = first_subnode[p]; c1 = c0 + nchild[p]; }
+    else if (p == 0) { c0 = 0; c1 = 1; }
+    else return;
+    auto is_leaf = [&](int64_t j) { return nchild[j] == 0 && nmass[j] != 0.0; };
+    int64_t j = c0;
+    while (j < c1) {
+        if (!is_leaf(j)) { ++j; continue; }
+        int64_t e = j + 1;
+        while (e < c1 && is_leaf(e)) ++e;
+        const int nl = (int)(e - j);
+        double ox = 0.0, oy = 0.0, oz = 0.0;
+        uint32_t total = 0;
+        for (int64_t k = j; k < e; ++k) {
+            ox += ncom[3 * k]; oy += ncom[3 * k + 1]; oz += ncom[3 * k + 2];
+            total += count[k];
+        }
+        ox /= nl; oy /= nl; oz /= nl;
+        if (nl > 1) {
+            NodeRec r = rec[j];
+            r.com[0] = ox; r.com[1] = oy; r.com[2] = oz;
+            r.kind = (int32_t)total;
+            r.next_branch = next_branch[e - 1];
+            r.nleaf = nl;
+            rec[j] = r;
+        }
+        if (src32) {
+            const uint32_t s0 = start[j];
+            for (uint32_t s = s0; s < s0 + total; ++s)
+                src32[s] = make_float4((float)(spos[3 * (int64_t)s] - ox), (float)(spos[3 * (int64_t)s + 1] - oy),
+                                       (float)(spos[3 * (int64_t)s + 2] - oz), smass ? (float)smass[s] : 1.0f);
+        }
+        j = e;
+    }
 }
 __global__ void update_gates(const double* __restrict__ hmax, double csep, int64_t nn, NodeRec* __restrict__ rec) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -714,11 +749,10 @@ void build_mass_payload(pnbx_tree_impl& t, cudaStream_t s, StageTimer& tm) {
     PNBX_LAUNCH(build_walk_records, nblk(nn), 256, 0, s, t.nmass.p, t.ncom.p, t.half.p, t.has_hmax ? t.hmax.p : nullptr,
                 t.kernel == PNBX_KERNEL_SPLINE ? 1.0 : 2.8, t.node_nchild.p, t.node_start.p, t.node_count.p,
                 t.first_subnode.p, t.next_branch.p, nn, t.rec.p);
-    if (t.n > 0) {
-        if (!t.src32.p) t.src32.alloc((size_t)t.n, s);
-        PNBX_LAUNCH(leaf_local_sources, nblk(nn), 256, 0, s, t.node_nchild.p, t.node_start.p, t.node_count.p, t.ncom.p,
-                    t.spos.p, t.has_mass ? t.smass.p : nullptr, nn, t.src32.p);
-    }
+    if (t.n > 0 && !t.src32.p) t.src32.alloc((size_t)t.n, s);
+    PNBX_LAUNCH(merge_leaf_runs, nblk(nn), 256, 0, s, t.node_nchild.p, t.first_subnode.p, t.node_start.p, t.node_count.p,
+                t.next_branch.p, t.nmass.p, t.ncom.p, t.spos.p, t.has_mass ? t.smass.p : nullptr, nn, t.rec.p,
+                t.n > 0 ? t.src32.p : nullptr);
     t.rec32 = mp::fast_rec_floats(t.order);
     t.moments32.alloc((size_t)nn * t.rec32, s);
     PNBX_LAUNCH(pack_walk_moments, nblk(nn), 256, 0, s, t.moments.p, nn, t.order, t.n_moments, t.rec32, t.moments32.p);

@@ -24,6 +24,10 @@ namespace {
 #define PNBX_WALK_MINB 12  // 40 registers: 48 of 64 warps resident (measured best for potentials, profiles/)
 #endif
 constexpr int WT = PNBX_WT;  // threads per block (independent warps)
+#ifndef PNBX_LEAF_UNROLL
+#define PNBX_LEAF_UNROLL 2  // measured: 2 and 4 ~2 % ahead of 1 once sibling leaves are merged into runs
+#endif
+constexpr int LEAF_UNROLL = PNBX_LEAF_UNROLL;  // pass-1 leaf loop unroll (leaves hold <= leaf_capacity particles)
 
 template <class T>
 struct Vec4T {
@@ -40,7 +44,7 @@ struct WalkArgs {
     const void* src;      // float4 (T=float) or double spos/smass (T=double)
     const double* spos;   // sorted float64 positions
     const double* smass;  // sorted float64 masses (nullable -> 1)
-    const T* src_h;       // sorted softenings in T (nullable)
+    const T* src_h;       // sorted softenings (nullable): float64 as given (T=double), max(h,0)^2 in float32 (T=float)
     const double* sh;     // sorted softenings float64 (nullable)
     const uint32_t* perm; // sorted position -> original index
     // targets
@@ -78,6 +82,92 @@ __device__ __forceinline__ T w2p_in(T u) {  // kernel.rs:108-124, u < 1
     T u2 = u * u;
     if (u < T(0.5)) return u * (T(32.0 / 3.0) + u2 * (T(32.0) * u - T(192.0 / 5.0)));
     return T(-1.0 / 15.0) / u2 + u * (T(64.0 / 3.0) + u * (T(-48.0) + u * (T(192.0 / 5.0) - T(32.0 / 3.0) * u)));
+}
+
+// fp32, branch-free W2 terms of one pair with r < h (kernel.rs:84-124): u = r/h, 1/u = h/r, both polynomial
+// branches evaluated and selected (no divergence, no IEEE division). kpot = W2(u)/h, kacc = W2'(u)/(h^2 r).
+// The unselected branch may overflow for r -> 0; it is discarded by the select.
+__device__ __forceinline__ void w2_terms_f32(float r2t, float rinv, float h, float hinv, float& kpot, float& kacc) {
+    const float u = r2t * rinv * hinv, uinv = h * rinv, u2 = u * u;
+    const bool lo = u < 0.5f;
+    const float wi = fmaf(u2, fmaf(u2, fmaf(6.4f, u, -9.6f), 16.0f / 3.0f), -2.8f);
+    const float wo = fmaf(u2, fmaf(u, fmaf(u, fmaf(-32.0f / 15.0f, u, 9.6f), -16.0f), 32.0f / 3.0f),
+                          fmaf(1.0f / 15.0f, uinv, -3.2f));
+    kpot = (lo ? wi : wo) * hinv;
+    const float pi = u * fmaf(u2, fmaf(32.0f, u, -38.4f), 32.0f / 3.0f);
+    const float po = fmaf(u, fmaf(u, fmaf(u, fmaf(-32.0f / 3.0f, u, 38.4f), -48.0f), 64.0f / 3.0f),
+                          (-1.0f / 15.0f) * uinv * uinv);
+    kacc = (lo ? pi : po) * (hinv * hinv) * rinv;
+}
+
+// ---- fp32 leaf sums (tree.rs:97-417). `sp` = the leaf's sources relative to the leaf's COM, `h2p` = their clamped
+// softenings SQUARED (max(h,0)^2; h = max(h_source, h_target) <=> h^2 = max of the squares), (lx,ly,lz) = the target in
+// the same frame, th2 = the target's clamped softening squared, skip_rel = index of the target itself inside this leaf
+// (anything outside [0,n) if it is not here: skip_self by index, tree.rs:130).
+// Pass 1, branch-free: every pair as Newtonian / Plummer. For the spline kernel, pairs with r < h contribute nothing
+// here and are flagged through the return value (true: this lane has at least one such pair) ...
+template <int WANT, int SMODE, bool CHECK>
+__device__ __forceinline__ bool leaf_pass1_f32(const float4* __restrict__ sp, const float* __restrict__ h2p, int n,
+                                               int skip_rel, float lx, float ly, float lz, float th2, float& pot,
+                                               float& ax, float& ay, float& az) {
+    float margin = 0.f;  // min over pairs of r^2 - h^2, clipped at 0
+#pragma unroll LEAF_UNROLL
+    for (int i = 0; i < n; ++i) {
+        const float4 s = __ldg(sp + i);
+        const float dx = s.x - lx, dy = s.y - ly, dz = s.z - lz;
+        float r2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, FLT_MIN)));  // + R2_TINY (tree.rs:139)
+        float m = s.w;
+        if (CHECK && i == skip_rel) {  // the target itself: contributes exactly nothing
+            m = 0.f;
+            r2 = 1e30f;
+        }
+        if (SMODE != 0) {
+            const float h2 = fmaxf(__ldg(h2p + i), th2);  // tree.rs:234-235
+            if (SMODE == 2) {
+                const float d = r2 - h2;  // < 0: inside the spline radius, left to pass 2 (no add-then-subtract)
+                margin = fminf(margin, d);
+                m = d < 0.f ? 0.f : m;
+            } else {
+                r2 += h2;  // Plummer: -1/sqrt(r^2+h^2); h = 0 is Newtonian
+            }
+        }
+        const float rinv = mp::inv_sqrt<float>(r2);
+        const float mr = m * rinv;
+        if (WANT & PNBX_WANT_POT) pot -= mr;
+        if (WANT & PNBX_WANT_ACC) {
+            const float mg = mr * (rinv * rinv);
+            ax = fmaf(dx, mg, ax);
+            ay = fmaf(dy, mg, ay);
+            az = fmaf(dz, mg, az);
+        }
+    }
+    return margin < 0.f;
+}
+// ... and pass 2 adds the W2-kernel terms of exactly those pairs (tree.rs:237-243 / 367-378), branch-free: all lanes
+// that enter run every pair, pairs outside their radius select 0.
+template <int WANT>
+__device__ __forceinline__ void leaf_pass2_f32(const float4* __restrict__ sp, const float* __restrict__ h2p, int n,
+                                               int skip_rel, float lx, float ly, float lz, float th2, float& pot,
+                                               float& ax, float& ay, float& az) {
+#pragma unroll 2
+    for (int i = 0; i < n; ++i) {
+        const float4 s = __ldg(sp + i);
+        const float h2 = fmaxf(__ldg(h2p + i), th2);
+        const float dx = s.x - lx, dy = s.y - ly, dz = s.z - lz;
+        const float r2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, FLT_MIN)));
+        const float d = r2 - h2;  // the same expression as pass 1: the two passes partition the pairs
+        const bool in = (d < 0.f) && (i != skip_rel);
+        const float rinv = mp::inv_sqrt<float>(r2), hinv = mp::inv_sqrt<float>(h2);
+        float kpot, kacc;
+        w2_terms_f32(r2, rinv, h2 * hinv, hinv, kpot, kacc);
+        if (WANT & PNBX_WANT_POT) pot = fmaf(s.w, in ? kpot : 0.f, pot);
+        if (WANT & PNBX_WANT_ACC) {
+            const float mg = s.w * (in ? kacc : 0.f);
+            ax = fmaf(dx, mg, ax);
+            ay = fmaf(dy, mg, ay);
+            az = fmaf(dz, mg, az);
+        }
+    }
 }
 
 // source particle p in T: float relative to its leaf's COM, double relative to the root centre
@@ -125,6 +215,7 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
     }
     const T fx = (T)(tx - a.rc[0]), fy = (T)(ty - a.rc[1]), fz = (T)(tz - a.rc[2]);
     const T th = (T)fmax(th64, 0.0);  // clamped target softening (tree.rs:115)
+    const float th2 = (float)th * (float)th;  // fp32 leaf sums compare squared softenings
     const bool soft = SMODE == 0 ? false : SMODE == 3 ? a.src_h != nullptr : true;  // softenings_opt.is_some() (tree.rs:116)
     const bool spline = SMODE == 3 ? a.kernel == PNBX_KERNEL_SPLINE : SMODE == 2;
     const bool gated = SMODE == 0 ? false : a.gated != 0;
@@ -146,77 +237,90 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
         const NodeRec c = a.rec[idx];  // one 64-byte record: one memory round trip per visit
         const NodeRec& gm = c;
         if (!active && resume == idx) active = true;
-        if (WANT == 0) {
-            if (active) ++n_visit;
-            if ((threadIdx.x & 31) == 0) ++n_wvisit;  // nodes the WARP visits: union of its lanes' paths
+        if (WANT == 0) {  // a leaf-run record stands for `nleaf` reference nodes (tree.cuh)
+            const int nodes = c.kind >= 0 ? c.nleaf : 1;
+            if (active) n_visit += nodes;
+            if ((threadIdx.x & 31) == 0) n_wvisit += nodes;  // nodes the WARP visits: union of its lanes' paths
         }
         if (c.kind == -2) {  // zero mass: skip the subtree (tree.rs:1087-1090)
             idx = c.next_branch;
             continue;
         }
-        if (c.kind >= 0) {  // leaf: always summed directly (tree.rs:1094-1112)
+        if (c.kind >= 0) {  // leaf (or a run of sibling leaves, tree.cuh): always summed directly (tree.rs:1094-1112)
             if (WANT == 0) {
-                if (active) { ++n_leaf; n_leafp += c.kind; }
+                if (active) { n_leaf += c.nleaf; n_leafp += c.kind; }
             } else if (active) {
-                T pot = T(0), ax = T(0), ay = T(0), az = T(0);
-                T lx = fx, ly = fy, lz = fz;
-                if (sizeof(T) == 4) {  // fp32 sources are stored relative to their leaf's COM
-                    lx = (T)(tx - gm.com[0]); ly = (T)(ty - gm.com[1]); lz = (T)(tz - gm.com[2]);
-                }
-                // Pass 1, branch-free: every pair as Newtonian / Plummer. For the spline kernel pairs with r < h
-                // (rare: the target's own and touching leaves) are only flagged here ...
-                bool inside = false;
-                for (int p = c.first; p < c.first + c.kind; ++p) {
-                    Vec4T<T> s = load_src<T>(a, p);
-                    const T dx = s.x - lx, dy = s.y - ly, dz = s.z - lz;
-                    T r2 = fma(dx, dx, fma(dy, dy, dz * dz));
-                    if (p == skip) {  // skip_self by index (tree.rs:130): contributes exactly nothing
-                        s.w = T(0);
-                        r2 = T(1);
-                    }
-                    if (soft) {
-                        const T h = max(max(a.src_h[p], T(0)), th);  // tree.rs:234-235
-                        if (spline) {
-                            const bool in = r2 < h * h;  // h > 0 is implied by r2 >= 0
-                            inside |= in;
-                            if (in) s.w = T(0);          // left to pass 2 (no add-then-subtract cancellation)
-                        } else {
-                            r2 = fma(h, h, r2);          // Plummer: -1/sqrt(r^2+h^2); h = 0 is Newtonian
-                        }
-                    }
-                    const T rinv = mp::inv_sqrt<T>(r2 + tiny_v<T>());
-                    const T mr = s.w * rinv;
-                    if (WANT & PNBX_WANT_POT) pot -= mr;
-                    if (WANT & PNBX_WANT_ACC) {
-                        const T mg = mr * (rinv * rinv);
-                        ax = fma(dx, mg, ax);
-                        ay = fma(dy, mg, ay);
-                        az = fma(dz, mg, az);
-                    }
-                }
-                // ... and pass 2 adds their W2-kernel terms (tree.rs:237-243 / 367-378)
-                if (spline && inside) {
+                if constexpr (sizeof(T) == 4) {
+                    // fp32: sources are stored relative to their leaf run's origin (close pairs keep their separation)
+                    float pot = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+                    const float lx = (float)(tx - gm.com[0]), ly = (float)(ty - gm.com[1]), lz = (float)(tz - gm.com[2]);
+                    const float4* sp = reinterpret_cast<const float4*>(a.src) + c.first;
+                    const float* h2p = SMODE != 0 ? a.src_h + c.first : nullptr;
+                    const int skip_rel = skip - c.first;
+                    bool inside;
+                    if ((unsigned)skip_rel < (unsigned)c.kind)  // the target's own leaf: the loop with the index check
+                        inside = leaf_pass1_f32<WANT, SMODE, true>(sp, h2p, c.kind, skip_rel, lx, ly, lz, th2, pot, ax, ay, az);
+                    else
+                        inside = leaf_pass1_f32<WANT, SMODE, false>(sp, h2p, c.kind, skip_rel, lx, ly, lz, th2, pot, ax, ay, az);
+                    if (SMODE == 2 && inside) leaf_pass2_f32<WANT>(sp, h2p, c.kind, skip_rel, lx, ly, lz, th2, pot, ax, ay, az);
+                    if (WANT & PNBX_WANT_POT) P += (double)pot;
+                    if (WANT & PNBX_WANT_ACC) { Ax += (double)ax; Ay += (double)ay; Az += (double)az; }
+                } else {
+                    // float64 verification mode: sources relative to the root centre, runtime softening mode
+                    T pot = T(0), ax = T(0), ay = T(0), az = T(0);
+                    const T lx = fx, ly = fy, lz = fz;
+                    bool inside = false;
                     for (int p = c.first; p < c.first + c.kind; ++p) {
-                        if (p == skip) continue;
-                        const Vec4T<T> s = load_src<T>(a, p);
-                        const T h = max(max(a.src_h[p], T(0)), th);
+                        Vec4T<T> s = load_src<T>(a, p);
                         const T dx = s.x - lx, dy = s.y - ly, dz = s.z - lz;
-                        const T r2 = fma(dx, dx, fma(dy, dy, dz * dz));
-                        if (!(r2 < h * h)) continue;
+                        T r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                        if (p == skip) {  // skip_self by index (tree.rs:130): contributes exactly nothing
+                            s.w = T(0);
+                            r2 = T(1);
+                        }
+                        if (soft) {
+                            const T h = max(max(a.src_h[p], T(0)), th);  // tree.rs:234-235
+                            if (spline) {
+                                const bool in = r2 < h * h;  // h > 0 is implied by r2 >= 0
+                                inside |= in;
+                                if (in) s.w = T(0);          // left to pass 2 (no add-then-subtract cancellation)
+                            } else {
+                                r2 = fma(h, h, r2);          // Plummer: -1/sqrt(r^2+h^2); h = 0 is Newtonian
+                            }
+                        }
                         const T rinv = mp::inv_sqrt<T>(r2 + tiny_v<T>());
-                        const T hinv = T(1) / h;
-                        const T u = (r2 + tiny_v<T>()) * rinv * hinv;
-                        if (WANT & PNBX_WANT_POT) pot = fma(s.w, w2_in(u) * hinv, pot);
+                        const T mr = s.w * rinv;
+                        if (WANT & PNBX_WANT_POT) pot -= mr;
                         if (WANT & PNBX_WANT_ACC) {
-                            const T mg = s.w * (w2p_in(u) * (hinv * hinv) * rinv);
+                            const T mg = mr * (rinv * rinv);
                             ax = fma(dx, mg, ax);
                             ay = fma(dy, mg, ay);
                             az = fma(dz, mg, az);
                         }
                     }
+                    if (spline && inside) {  // pass 2: the W2-kernel terms of the pairs with r < h (tree.rs:237-243 / 367-378)
+                        for (int p = c.first; p < c.first + c.kind; ++p) {
+                            if (p == skip) continue;
+                            const Vec4T<T> s = load_src<T>(a, p);
+                            const T h = max(max(a.src_h[p], T(0)), th);
+                            const T dx = s.x - lx, dy = s.y - ly, dz = s.z - lz;
+                            const T r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                            if (!(r2 < h * h)) continue;
+                            const T rinv = mp::inv_sqrt<T>(r2 + tiny_v<T>());
+                            const T hinv = T(1) / h;
+                            const T u = (r2 + tiny_v<T>()) * rinv * hinv;
+                            if (WANT & PNBX_WANT_POT) pot = fma(s.w, w2_in(u) * hinv, pot);
+                            if (WANT & PNBX_WANT_ACC) {
+                                const T mg = s.w * (w2p_in(u) * (hinv * hinv) * rinv);
+                                ax = fma(dx, mg, ax);
+                                ay = fma(dy, mg, ay);
+                                az = fma(dz, mg, az);
+                            }
+                        }
+                    }
+                    if (WANT & PNBX_WANT_POT) P += (double)pot;
+                    if (WANT & PNBX_WANT_ACC) { Ax += (double)ax; Ay += (double)ay; Az += (double)az; }
                 }
-                if (WANT & PNBX_WANT_POT) P += (double)pot;
-                if (WANT & PNBX_WANT_ACC) { Ax += (double)ax; Ay += (double)ay; Az += (double)az; }
             }
             idx = c.next_branch;
             continue;
@@ -236,7 +340,7 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
             if (sizeof(T) == 4) {
                 // fp32: contracted closed forms on the per-node fp32 record (multipole.cuh m2p_fast / m2p_fast45)
                 float pot = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-                const float* rec = reinterpret_cast<const float*>(a.moments) + (int64_t)idx * a.K;
+                const float* rec = reinterpret_cast<const float*>(a.moments) + (int64_t)idx * mp::fast_rec_floats(ORDER);
                 if (ORDER <= 3) mp::m2p_fast<(ORDER <= 3 ? ORDER : 3), (WANT == 0 ? 1 : WANT)>(rec, (float)dx, (float)dy, (float)dz, pot, ax, ay, az);
                 else mp::m2p_fast45<(ORDER >= 4 ? ORDER : 4), (WANT == 0 ? 1 : WANT)>(rec, (float)dx, (float)dy, (float)dz, pot, ax, ay, az);
                 if (WANT & PNBX_WANT_POT) P += (double)pot;
