@@ -330,10 +330,13 @@ __device__ __forceinline__ void m2p_accel(const T* M, const T* D, T& ax, T& ay, 
 //   a   =  M d/r^3 + ((15 s - 3 trS) u - 6 S u)/r^4          (dipole about the COM is rounding noise: dropped)
 // with S the symmetric second-moment matrix (S_xx = m200, S_xy = m110/2, ...), s = u.S.u,
 // C(u) = sum_{l+m+n=3} M_lmn u^lmn, w_x = 3 m300 + m120 + m102 (cyclic).
-// Per-node record (float): [0] M, [1..6] 6S (xx,yy,zz,xy,xz,yz), [7] 3 trS, [8..17] octupole (field order),
-// [18..20] 3w, [21..23] pad.  REC = 1 (order<=1), 8 (order 2), 24 (order 3).
+// Because |u| = 1 the trace and the w terms fold into the forms themselves: with the traceless T = 3 (S - trS/3 I)
+// and the cubic C'(u) = 15 C(u) - 3 (w.u)(u.u) (coefficients precomputed per node in float64, pack_walk_moments)
+//   phi = -M/r - (u.T.u)/r^3 + C'(u)/r^4          a = M d/r^3 + 2 (2.5 (u.T.u) u - T u)/r^4
+// Per-node record (float): [0] M, [1..6] T (xx,yy,zz,xy,xz,yz), [7] pad, [8..17] C' (x3 y3 z3 x2y | x2z xy2 xz2 y2z |
+// yz2 xyz), [18,19] pad.  Floats per node: 1 (order<=1), 8 (order 2), 20 (order 3). Orders 4, 5: see m2p_fast45.
 __host__ __device__ constexpr int fast_rec_floats(int order) {
-    return order <= 1 ? 1 : order == 2 ? 8 : order == 3 ? 24 : order == 4 ? 48 : 84;
+    return order <= 1 ? 1 : order == 2 ? 8 : order == 3 ? 20 : order == 4 ? 48 : 84;
 }
 
 template <int ORDER, int WANT>
@@ -351,38 +354,34 @@ __device__ __forceinline__ void m2p_fast(const float* __restrict__ rec, float dx
     const float4 r0 = __ldg(reinterpret_cast<const float4*>(rec));
     const float M = r0.x;
     const bool need_quad = (WANT & 1) || ORDER >= 3;
-    float ux = dx * ri, uy = dy * ri, uz = dz * ri;
-    float qx = 0.f, qy = 0.f, qz = 0.f, s6 = 0.f, tr3 = 0.f;
+    const float ux = dx * ri, uy = dy * ri, uz = dz * ri;
+    float qx = 0.f, qy = 0.f, qz = 0.f, st = 0.f;
     if (need_quad) {
         const float4 r1 = __ldg(reinterpret_cast<const float4*>(rec) + 1);
-        const float Sxx = r0.y, Syy = r0.z, Szz = r0.w, Sxy = r1.x, Sxz = r1.y, Syz = r1.z;
-        tr3 = r1.w;
-        qx = fmaf(Sxz, uz, fmaf(Sxy, uy, Sxx * ux));  // 6 S u
-        qy = fmaf(Syz, uz, fmaf(Syy, uy, Sxy * ux));
-        qz = fmaf(Szz, uz, fmaf(Syz, uy, Sxz * ux));
-        s6 = fmaf(qz, uz, fmaf(qy, uy, qx * ux));     // 6 u.S.u
+        const float Txx = r0.y, Tyy = r0.z, Tzz = r0.w, Txy = r1.x, Txz = r1.y, Tyz = r1.z;
+        qx = fmaf(Txz, uz, fmaf(Txy, uy, Txx * ux));  // T u
+        qy = fmaf(Tyz, uz, fmaf(Tyy, uy, Txy * ux));
+        qz = fmaf(Tzz, uz, fmaf(Tyz, uy, Txz * ux));
+        st = fmaf(qz, uz, fmaf(qy, uy, qx * ux));     // u.T.u = 3 s - trS
     }
     if (WANT & 1) {
         float phi = -M * ri;
-        phi = fmaf(-ri3, fmaf(0.5f, s6, -(1.f / 3.f) * tr3), phi);  // -(3 s - trS)/r^3
+        phi = fmaf(-ri3, st, phi);
         if (ORDER >= 3) {
             const float4 r2v = __ldg(reinterpret_cast<const float4*>(rec) + 2);
             const float4 r3v = __ldg(reinterpret_cast<const float4*>(rec) + 3);
             const float4 r4v = __ldg(reinterpret_cast<const float4*>(rec) + 4);
-            // octupole in field order: m300 m030 m003 m210 | m201 m120 m102 m021 | m012 m111 3wx 3wy | 3wz
-            const float m300 = r2v.x, m030 = r2v.y, m003 = r2v.z, m210 = r2v.w;
-            const float m201 = r3v.x, m120 = r3v.y, m102 = r3v.z, m021 = r3v.w;
-            const float m012 = r4v.x, m111 = r4v.y, wx3 = r4v.z, wy3 = r4v.w;
-            const float wz3 = __ldg(rec + 20);
-            const float cx = fmaf(m201, uz, fmaf(m210, uy, m300 * ux));
-            const float cy = fmaf(m021, uz, fmaf(m120, ux, m030 * uy));
-            const float cz = fmaf(m012, uy, fmaf(m102, ux, m003 * uz));
+            const float c300 = r2v.x, c030 = r2v.y, c003 = r2v.z, c210 = r2v.w;
+            const float c201 = r3v.x, c120 = r3v.y, c102 = r3v.z, c021 = r3v.w;
+            const float c012 = r4v.x, c111 = r4v.y;
+            const float cx = fmaf(c201, uz, fmaf(c210, uy, c300 * ux));
+            const float cy = fmaf(c021, uz, fmaf(c120, ux, c030 * uy));
+            const float cz = fmaf(c012, uy, fmaf(c102, ux, c003 * uz));
             float C = (ux * ux) * cx;
             C = fmaf(uy * uy, cy, C);
             C = fmaf(uz * uz, cz, C);
-            C = fmaf(m111 * ux, uy * uz, C);
-            const float wu3 = fmaf(wz3, uz, fmaf(wy3, uy, wx3 * ux));
-            phi = fmaf(ri2 * ri2, fmaf(15.f, C, -wu3), phi);
+            C = fmaf(c111 * ux, uy * uz, C);
+            phi = fmaf(ri2 * ri2, C, phi);
         }
         pot = phi;
     }
@@ -390,11 +389,11 @@ __device__ __forceinline__ void m2p_fast(const float* __restrict__ rec, float dx
         const float g = M * ri3;
         ax = g * dx; ay = g * dy; az = g * dz;
         if (ORDER >= 3) {
-            const float ri4 = ri2 * ri2;
-            const float c1 = fmaf(2.5f, s6, -tr3);  // 15 s - 3 trS
-            ax = fmaf(ri4, fmaf(c1, ux, -qx), ax);
-            ay = fmaf(ri4, fmaf(c1, uy, -qy), ay);
-            az = fmaf(ri4, fmaf(c1, uz, -qz), az);
+            const float ri4x2 = (ri2 + ri2) * ri2;
+            const float c1 = 2.5f * st;
+            ax = fmaf(ri4x2, fmaf(c1, ux, -qx), ax);
+            ay = fmaf(ri4x2, fmaf(c1, uy, -qy), ay);
+            az = fmaf(ri4x2, fmaf(c1, uz, -qz), az);
         }
     }
 }
@@ -406,7 +405,8 @@ __device__ __forceinline__ void m2p_fast(const float* __restrict__ rec, float dx
 //   Psi_2 = (3 S(u,u) - trS) / r^3                        Psi_3 = (-15 C(u) + 9 v.u) / r^4
 //   Psi_4 = (105 Q(u) - 7.5 LapQ(u) + 0.375 Lap2Q) / r^5   Psi_5 = (-945 R(u) + 52.5 LapR(u) - 1.875 Lap2R.u) / r^6
 //   phi = -(M/r + Psi_2 + ... + Psi_order)                  a = -grad_d (M/r + Psi_2 + ... + Psi_(order-1))
-// The Laplacians' coefficients are precomputed per node (pack_walk_moments). Record (floats): [0..23] the order-3 record,
+// The Laplacians' coefficients are precomputed per node (pack_walk_moments). Record (floats): [0] M, [1..6] 6S (xx,yy,zz,
+// xy,xz,yz), [7] 3 trS, [8..17] octupole (field order), [18..20] 9 v = 3 w, [21..23] pad,
 // [24..38] Q (m400..m112, field order), [39..44] LapQ as a quadratic form (xx,yy,zz,xy,xz,yz), [45] Lap2Q, [46,47] pad,
 // [48..68] R (m500..m113), [69..78] LapR as a cubic (x3,y3,z3,x2y,x2z,xy2,xz2,y2z,yz2,xyz), [79..81] Lap2R, [82,83] pad.
 template <int ORDER, int WANT>

@@ -495,17 +495,35 @@ __global__ void pack_walk_moments(const double* __restrict__ mom, int64_t nn, in
     using namespace mp;
     if (order <= 1) { o[0] = (float)m[I000]; return; }
     o[0] = (float)m[I000];
+    if (order <= 3) {  // m2p_fast layout: traceless T = 3 (S - trS/3 I), folded cubic C' = 15 C - 3 (w.u)(u.u)
+        const double tr = m[I200] + m[I020] + m[I002];
+        o[1] = (float)(3.0 * m[I200] - tr); o[2] = (float)(3.0 * m[I020] - tr); o[3] = (float)(3.0 * m[I002] - tr);
+        o[4] = (float)(1.5 * m[I110]); o[5] = (float)(1.5 * m[I101]); o[6] = (float)(1.5 * m[I011]);
+        o[7] = 0.f;
+        if (order == 3) {
+            const double wx = 3.0 * m[I300] + m[I120] + m[I102];
+            const double wy = 3.0 * m[I030] + m[I210] + m[I012];
+            const double wz = 3.0 * m[I003] + m[I201] + m[I021];
+            // field order: 300 030 003 210 201 120 102 021 012 111; the w component is that of the odd-power axis
+            o[8]  = (float)(15.0 * m[I300] - 3.0 * wx); o[9]  = (float)(15.0 * m[I030] - 3.0 * wy);
+            o[10] = (float)(15.0 * m[I003] - 3.0 * wz); o[11] = (float)(15.0 * m[I210] - 3.0 * wy);
+            o[12] = (float)(15.0 * m[I201] - 3.0 * wz); o[13] = (float)(15.0 * m[I120] - 3.0 * wx);
+            o[14] = (float)(15.0 * m[I102] - 3.0 * wx); o[15] = (float)(15.0 * m[I021] - 3.0 * wz);
+            o[16] = (float)(15.0 * m[I012] - 3.0 * wy); o[17] = (float)(15.0 * m[I111]);
+            o[18] = o[19] = 0.f;
+        }
+        return;
+    }
+    // orders 4, 5 (m2p_fast45): [1..6] 6S, [7] 3 trS, [8..17] octupole, [18..20] 9 v = 3 w
     o[1] = (float)(6.0 * m[I200]); o[2] = (float)(6.0 * m[I020]); o[3] = (float)(6.0 * m[I002]);
     o[4] = (float)(3.0 * m[I110]); o[5] = (float)(3.0 * m[I101]); o[6] = (float)(3.0 * m[I011]);
     o[7] = (float)(3.0 * (m[I200] + m[I020] + m[I002]));
-    if (order >= 3) {
-        for (int t = 0; t < 10; ++t) o[8 + t] = (float)m[I300 + t];
-        o[18] = (float)(3.0 * (3.0 * m[I300] + m[I120] + m[I102]));
-        o[19] = (float)(3.0 * (3.0 * m[I030] + m[I210] + m[I012]));
-        o[20] = (float)(3.0 * (3.0 * m[I003] + m[I201] + m[I021]));
-        o[21] = o[22] = o[23] = 0.f;
-    }
-    if (order >= 4) {  // m2p_fast45 layout: octupole slots [18..20] hold 9 v = 3 w (same numbers as above)
+    for (int t = 0; t < 10; ++t) o[8 + t] = (float)m[I300 + t];
+    o[18] = (float)(3.0 * (3.0 * m[I300] + m[I120] + m[I102]));
+    o[19] = (float)(3.0 * (3.0 * m[I030] + m[I210] + m[I012]));
+    o[20] = (float)(3.0 * (3.0 * m[I003] + m[I201] + m[I021]));
+    o[21] = o[22] = o[23] = 0.f;
+    if (order >= 4) {
         for (int t = 0; t < 15; ++t) o[24 + t] = (float)m[I400 + t];
         o[39] = (float)(12.0 * m[I400] + 2.0 * m[I220] + 2.0 * m[I202]);
         o[40] = (float)(12.0 * m[I040] + 2.0 * m[I220] + 2.0 * m[I022]);
