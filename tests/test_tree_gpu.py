@@ -408,3 +408,36 @@ def test_concurrent_queries_on_one_tree_from_threads():
     for t in ts:
         t.join()
     assert not errs and all(out[k] for k in range(6))
+
+
+@pytest.mark.parametrize("cap", [1, 3, 8, 32])
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_leaf_runs_dense_softened_core(cap, kernel):
+    # A core whose softening exceeds the inter-particle spacing: the hmax gate (tree.rs:55-71) opens whole
+    # subtrees, most work is direct leaf sums with r < h. The walk merges sibling leaves into runs and sums
+    # them in fp32 with squared softenings (tree_walk.cu); lists and results must still be the reference's.
+    n = 6000
+    pos, m = hernquist(n, seed=131, a=0.05)
+    rng = np.random.default_rng(132)
+    h = np.where(rng.uniform(size=n) < 0.5, 0.02, rng.uniform(1e-4, 5e-2, n))
+    g = R().Octree(pos, m, cap, 3, h, kernel)
+    o = O.Tree(pos, m, cap, 3, h, kernel)
+    assert_same_topology(g, o)
+    p_o, a_o = o.eval(0.7)
+    c_o = o.eval(0.7, want=1, counters=True)[2]  # one traversal (want=3 would count the pot and acc walks)
+    c_g = g.walk_counters(0.7)
+    assert {k: c_g[k] for k in c_o} == c_o
+    assert c_o["leaf_particles"] > 50 * n  # the regime this test is about
+    p64, a64 = g._eval(None, 0.7, 3, precision="f64")
+    assert rms_rel(p64, p_o) < TOL64 and rms_rel_vec(a64, a_o) < TOL64
+    p32, a32 = g._eval(None, 0.7, 3)
+    assert rms_rel(p32, p_o) < TOL32 and rms_rel_vec(a32, a_o) < TOL32
+    assert np.abs((p32 - p_o) / p_o).max() < 20 * TOL32
+    # single-output kernels agree with the fused one to fp32 rounding
+    p1 = g.compute_potentials(0.7)
+    a2 = g.compute_accelerations(0.7)
+    assert rms_rel(p1, p_o) < TOL32 and rms_rel_vec(a2, a_o) < TOL32
+    q = pos[:400] + rng.normal(0.0, 1e-3, (400, 3))
+    p_q, a_q = o.eval(0.7, targets=q)
+    p32, a32 = g._eval(q, 0.7, 3)
+    assert rms_rel(p32, p_q) < TOL32 and rms_rel_vec(a32, a_q) < TOL32
