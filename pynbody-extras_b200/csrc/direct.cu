@@ -14,6 +14,7 @@
 #include <cfloat>
 
 #include "common.cuh"
+#include "spline.cuh"
 
 namespace pnbx {
 namespace {
@@ -516,6 +517,231 @@ direct_kernel_f2(const Pair8* __restrict__ src, int64_t n_src, const Vec4<float>
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed-FP32x2 variant for PER-PAIR softening h = max(h_i, h_j) (direct.rs:370-658), valid when every softening that
+// takes part is >= 0 so that h^2 = max(h_i^2, h_j^2): the sources carry their squared softening next to the pair
+// records (a second bulk copy per tile), the targets theirs in a register (0 for at-points targets: max(h_j, 0)).
+//   HMODE 1, Plummer:  r2 = |d|^2 + max(h_i^2, h_j^2): 2 FMNMX more than the constant-softening loop per pair record.
+//   HMODE 2, spline:   pass 1 = Newtonian sweep that zeroes the mass of pairs with r < h and flags them, pass 2 (only
+//                      when some lane of the warp flagged one) adds their W2 terms, as in the scalar kernel.
+// One scalar pair (diagonal / ragged tiles, and the spline's pass 2 with ONLY_INSIDE): same r2 chain as the packed loop.
+template <int WANT, int HMODE, bool ONLY_INSIDE>
+__device__ __forceinline__ void pair_h2_scalar(float xi, float yi, float zi, float th2, float sx, float sy, float sz,
+                                               float sm, float hs2, bool is_self, float& ax, float& ay, float& az,
+                                               float& pot) {
+    const float dx = sx - xi, dy = sy - yi, dz = sz - zi;
+    const float h2 = fmaxf(hs2, th2);
+    if (HMODE == 1) {
+        float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, fmaxf(h2, FLT_MIN))));
+        float m = sm;
+        if (is_self) { r2 = 1.f; m = 0.f; }
+        const float rinv = rsqrt_fast(r2);
+        const float mr = m * rinv;
+        if (WANT & PNBX_WANT_POT) pot -= mr;
+        if (WANT & PNBX_WANT_ACC) {
+            const float g = mr * (rinv * rinv);
+            ax = fmaf(dx, g, ax); ay = fmaf(dy, g, ay); az = fmaf(dz, g, az);
+        }
+    } else {
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, FLT_MIN)));
+        const bool in = r2 < h2;  // the packed pass-1 predicate, bit for bit
+        if (ONLY_INSIDE && !in) return;
+        if (is_self) return;
+        const float rinv = rsqrt_fast(r2);
+        float kpot = -rinv, kacc = rinv * rinv * rinv;
+        if (in) {
+            const float hinv = rsqrt_fast(h2);
+            w2_terms_f32(r2, rinv, h2 * hinv, hinv, kpot, kacc);
+        }
+        if (WANT & PNBX_WANT_POT) pot = fmaf(sm, kpot, pot);
+        if (WANT & PNBX_WANT_ACC) {
+            const float g = sm * kacc;
+            ax = fmaf(dx, g, ax); ay = fmaf(dy, g, ay); az = fmaf(dz, g, az);
+        }
+    }
+}
+
+template <int WANT, int HMODE>
+__global__ void __launch_bounds__(DT, PNBX_MINB)
+direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h2, int64_t n_src,
+                  const Vec4<float>* __restrict__ tgt, const float* __restrict__ tgt_h2, int64_t m, int64_t self_base,
+                  int tiles_per_split, double* __restrict__ out_pot, double* __restrict__ out_acc) {
+    __shared__ Pair8 s_src[STAGES][TILEP];
+    __shared__ alignas(16) float2 s_h2[STAGES][TILEP];
+    __shared__ alignas(8) uint64_t s_full[STAGES];
+    const int tid = threadIdx.x;
+    const int64_t n_pairs = (n_src + 1) / 2;  // the odd tail is padded (zero mass, far away, h = 0)
+    const int64_t n_tiles = (n_pairs + TILEP - 1) / TILEP;
+    const int64_t tile_begin = (int64_t)blockIdx.y * tiles_per_split;
+    const int64_t tile_end = tile_begin + tiles_per_split < n_tiles ? tile_begin + tiles_per_split : n_tiles;
+    const int64_t tgt_base = (int64_t)blockIdx.x * (DT * TPT);
+
+    f2_t xi[TPT], yi[TPT], zi[TPT];
+    float th2[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+        int64_t i = tgt_base + k * DT + tid;
+        if (i > m - 1) i = m - 1;
+        Vec4<float> t = tgt[i];
+        xi[k] = f2_pack(t.x, t.x); yi[k] = f2_pack(t.y, t.y); zi[k] = f2_pack(t.z, t.z);
+        th2[k] = tgt_h2 ? tgt_h2[i] : 0.f;
+    }
+    // global source index of this thread's k-th target: g0 + k*DT (lanes past the end are clamped duplicates whose
+    // results are never stored, so their index does not matter)
+    const int64_t g0 = self_base >= 0 ? self_base + tgt_base + tid : INT64_MIN / 2;
+    auto lo = [](f2_t v) { float a, b; f2_unpack(v, a, b); return a; };
+    const f2_t tiny2 = f2_pack(FLT_MIN, FLT_MIN);
+    double Ax[TPT], Ay[TPT], Az[TPT], P[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) Ax[k] = Ay[k] = Az[k] = P[k] = 0.0;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t tile) {
+        int st = (int)((tile - tile_begin) % STAGES);
+        int64_t q0 = tile * TILEP;
+        int cnt = (int)(n_pairs - q0 < TILEP ? n_pairs - q0 : TILEP);
+        uint32_t bytes = (uint32_t)cnt * sizeof(Pair8);
+        uint32_t hbytes = (uint32_t)((cnt * sizeof(float2) + 15) / 16 * 16);  // src_h2 is padded
+        mbar_expect_tx(&s_full[st], bytes + hbytes);
+        bulk_g2s(&s_src[st][0], src + q0, bytes, &s_full[st]);
+        bulk_g2s(&s_h2[st][0], src_h2 + 2 * q0, hbytes, &s_full[st]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < STAGES - 1; ++s)
+            if (tile_begin + s < tile_end) issue(tile_begin + s);
+
+    const int64_t blk_lo = self_base >= 0 ? self_base + tgt_base : INT64_MAX;
+    const int64_t blk_hi = self_base >= 0 ? blk_lo + DT * TPT : INT64_MIN;
+
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+        const int it = (int)(tile - tile_begin);
+        const int st = it % STAGES;
+        if (tid == 0 && tile + STAGES - 1 < tile_end) issue(tile + STAGES - 1);
+        mbar_wait(&s_full[st], (uint32_t)((it / STAGES) & 1));
+        const int64_t q0 = tile * TILEP;
+        const int cnt = (int)(n_pairs - q0 < TILEP ? n_pairs - q0 : TILEP);
+        const int64_t j0 = 2 * q0;
+        const bool diag = (j0 < blk_hi) && (j0 + 2 * cnt > blk_lo);
+        if (!diag && cnt == TILEP) {
+            f2_t ax[TPT], ay[TPT], az[TPT], p[TPT];
+#pragma unroll
+            for (int k = 0; k < TPT; ++k) ax[k] = ay[k] = az[k] = p[k] = 0ull;  // {+0.f, +0.f}
+            bool inside = false;
+#pragma unroll UNROLL_F2
+            for (int q = 0; q < TILEP; ++q) {
+                const ulonglong4 v = *reinterpret_cast<const ulonglong4*>(&s_src[st][q]);  // {x0x1, y0y1, z0z1, m0m1}
+                const float2 hh = s_h2[st][q];
+#pragma unroll
+                for (int k = 0; k < TPT; ++k) {
+                    const f2_t dx = f2_sub(v.x, xi[k]), dy = f2_sub(v.y, yi[k]), dz = f2_sub(v.z, zi[k]);
+                    const float h2a = fmaxf(hh.x, th2[k]), h2b = fmaxf(hh.y, th2[k]);
+                    f2_t r2 = f2_fma(dx, dx, HMODE == 1 ? f2_pack(fmaxf(h2a, FLT_MIN), fmaxf(h2b, FLT_MIN)) : tiny2);
+                    r2 = f2_fma(dy, dy, r2);
+                    r2 = f2_fma(dz, dz, r2);
+                    float ra, rb;
+                    f2_unpack(r2, ra, rb);
+                    f2_t mm = v.w;
+                    if (HMODE == 2) {
+                        float m0, m1;
+                        f2_unpack(v.w, m0, m1);
+                        const bool ia = ra < h2a, ib = rb < h2b;  // r < h: left to pass 2 (no add-then-subtract)
+                        inside |= ia | ib;
+                        mm = f2_pack(ia ? 0.f : m0, ib ? 0.f : m1);
+                    }
+                    const f2_t rinv = f2_pack(rsqrt_fast(ra), rsqrt_fast(rb));
+                    if (WANT & PNBX_WANT_POT) p[k] = f2_fma(mm, rinv, p[k]);
+                    if (WANT & PNBX_WANT_ACC) {
+                        const f2_t g = f2_mul(f2_mul(mm, rinv), f2_mul(rinv, rinv));
+                        ax[k] = f2_fma(dx, g, ax[k]);
+                        ay[k] = f2_fma(dy, g, ay[k]);
+                        az[k] = f2_fma(dz, g, az[k]);
+                    }
+                }
+            }
+            float sax[TPT], say[TPT], saz[TPT], sp[TPT];
+#pragma unroll
+            for (int k = 0; k < TPT; ++k) {
+                float a, b;
+                sax[k] = say[k] = saz[k] = sp[k] = 0.f;
+                if (WANT & PNBX_WANT_ACC) {
+                    f2_unpack(ax[k], a, b); sax[k] = a + b;
+                    f2_unpack(ay[k], a, b); say[k] = a + b;
+                    f2_unpack(az[k], a, b); saz[k] = a + b;
+                }
+                if (WANT & PNBX_WANT_POT) { f2_unpack(p[k], a, b); sp[k] = -(a + b); }
+            }
+            if (HMODE == 2 && __any_sync(0xffffffffu, inside)) {
+                if (inside) {
+                    for (int q = 0; q < TILEP; ++q) {
+                        const Pair8 pr = s_src[st][q];
+                        const float2 hh = s_h2[st][q];
+#pragma unroll
+                        for (int k = 0; k < TPT; ++k) {
+                            pair_h2_scalar<WANT, 2, true>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2[k], pr.x0, pr.y0, pr.z0, pr.m0, hh.x, false,
+                                                          sax[k], say[k], saz[k], sp[k]);
+                            pair_h2_scalar<WANT, 2, true>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2[k], pr.x1, pr.y1, pr.z1, pr.m1, hh.y, false,
+                                                          sax[k], say[k], saz[k], sp[k]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < TPT; ++k) {
+                if (WANT & PNBX_WANT_ACC) { Ax[k] += (double)sax[k]; Ay[k] += (double)say[k]; Az[k] += (double)saz[k]; }
+                if (WANT & PNBX_WANT_POT) P[k] += (double)sp[k];
+            }
+        } else {
+            // ragged tail and/or self-skip by index: scalar loop over the same pair records
+            float ax[TPT], ay[TPT], az[TPT], p[TPT];
+#pragma unroll
+            for (int k = 0; k < TPT; ++k) ax[k] = ay[k] = az[k] = p[k] = 0.f;
+            const int nsrc_tile = (int)((n_src - j0) < 2 * cnt ? (n_src - j0) : 2 * cnt);
+            for (int j = 0; j < nsrc_tile; ++j) {
+                const Pair8& pr = s_src[st][j >> 1];
+                const float2 hh = s_h2[st][j >> 1];
+                const bool odd = j & 1;
+                const float sx = odd ? pr.x1 : pr.x0, sy = odd ? pr.y1 : pr.y0, sz = odd ? pr.z1 : pr.z0;
+                const float sm = odd ? pr.m1 : pr.m0, hs2 = odd ? hh.y : hh.x;
+                const int64_t gj = j0 + j;
+#pragma unroll
+                for (int k = 0; k < TPT; ++k)
+                    pair_h2_scalar<WANT, HMODE, false>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2[k], sx, sy, sz, sm, hs2, gj == g0 + k * DT, ax[k],
+                                                       ay[k], az[k], p[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < TPT; ++k) {
+                if (WANT & PNBX_WANT_ACC) { Ax[k] += (double)ax[k]; Ay[k] += (double)ay[k]; Az[k] += (double)az[k]; }
+                if (WANT & PNBX_WANT_POT) P[k] += (double)p[k];
+            }
+        }
+        __syncthreads();
+    }
+    const int64_t split_off = (int64_t)blockIdx.y * m;
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+        int64_t i = tgt_base + k * DT + tid;
+        if (i < m) {
+            if (WANT & PNBX_WANT_POT) out_pot[split_off + i] = P[k];
+            if (WANT & PNBX_WANT_ACC) {
+                double* a = out_acc + 3 * (split_off + i);
+                a[0] = Ax[k]; a[1] = Ay[k]; a[2] = Az[k];
+            }
+        }
+    }
+}
+
+// squared clamped softenings for direct_kernel_f2h: out[i] = max(h_i, 0)^2, zero padding
+__global__ void pack_h2(const double* __restrict__ in, int64_t n, int64_t n_padded, float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_padded) return;
+    const float h = i < n ? (float)fmax(in[i], 0.0) : 0.f;
+    out[i] = h * h;
+}
+
 // float64 (n,3) positions + mass -> pair records relative to the bbox centre; an odd tail gets a
 // zero-mass partner far away (its r^2 is huge but finite: contributes exactly 0, never NaN).
 __global__ void pack_pairs(const double* __restrict__ pos, const double* __restrict__ mass, int64_t n,
@@ -639,8 +865,8 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     int soft = SOFT_NEWTON;
     T eps2 = sizeof(T) == 4 ? (T)FLT_MIN : (T)DBL_MIN;  // the reference's + R2_TINY
     bool pair_h = false;
+    double hmm[2] = {0.0, 0.0};  // min / max of the source softenings
     if (kernel == PNBX_KERNEL_PLUMMER || kernel == PNBX_KERNEL_SPLINE) {
-        double hmm[2] = {0.0, 0.0};
         if (d_h) {
             DevBuf<double> part(2 * 296, s), res(2, s);
             PNBX_LAUNCH(minmax_scalar_blocks, 296, 256, 0, s, d_h, n, part.get());
@@ -666,7 +892,13 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
         }
     }
 
-    const bool use_f2 = sizeof(T) == 4 && !pair_h && !getenv("PNBX_DIRECT_SCALAR");  // packed FFMA2 path
+    const bool f2_ok = sizeof(T) == 4 && !getenv("PNBX_DIRECT_SCALAR");
+    const bool use_f2 = f2_ok && !pair_h;  // packed FFMA2 path, constant softening
+    // packed per-pair path: needs h^2 = max(h_i^2, h_j^2), i.e. every softening that takes part >= 0. The spline clamps
+    // at 0 anyway (h <= 0 is Newtonian), at-points Plummer uses max(h_j, 0) (direct.rs:560); Plummer in self mode with a
+    // negative softening (max(h_i, h_j) of signed values) stays on the scalar kernel.
+    const bool use_f2h = f2_ok && pair_h && !getenv("PNBX_DIRECT_NO_F2H") &&
+                         (soft == SOFT_SPLINE || !self || hmm[0] >= 0.0);
     bool const_mass = false;
     double mass_value = 1.0;
     if (use_f2 && !getenv("PNBX_DIRECT_NO_CONSTM")) {
@@ -684,15 +916,21 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     }
     DevBuf<Vec4<T>> src4;
     DevBuf<Pair8> srcp;
-    if (use_f2) {
+    DevBuf<float> srch2;
+    if (use_f2 || use_f2h) {
         srcp.alloc((size_t)(n + 1) / 2, s);
         PNBX_LAUNCH(pack_pairs, (unsigned)ceil_div((n + 1) / 2, 256), 256, 0, s, d_pos, d_mass, n, bbox.get(), srcp.get());
+        if (use_f2h) {
+            const int64_t np = ((n + 1) / 2) * 2 + 4;  // whole pair records + room for the 16-byte rounding of the bulk copy
+            srch2.alloc((size_t)np, s);
+            PNBX_LAUNCH(pack_h2, (unsigned)ceil_div(np, 256), 256, 0, s, d_h, n, np, srch2.get());
+        }
     } else {
         src4.alloc((size_t)n, s);
         PNBX_LAUNCH(pack_points<T>, (unsigned)ceil_div(n, 256), 256, 0, s, d_pos, d_mass, n, bbox.get(), T(1), src4.get());
     }
     DevBuf<T> srch;
-    if (pair_h) {
+    if (pair_h && !use_f2h) {
         int64_t np = ceil_div(n, 4) * 4 + 4;  // padded to 16 B granules for the bulk copy
         srch.alloc((size_t)np, s);
         PNBX_LAUNCH(pack_scalar<T>, (unsigned)ceil_div(np, 256), 256, 0, s, d_h, n, np, soft == SOFT_SPLINE, srch.get());
@@ -700,7 +938,7 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     DevBuf<Vec4<T>> tgt4;
     const Vec4<T>* tgt_ptr;
     const T* tgt_h_ptr = nullptr;
-    if (self && !use_f2) {
+    if (self && !use_f2 && !use_f2h) {
         tgt_ptr = src4.get() + tgt_begin;
         if (pair_h) tgt_h_ptr = srch.get() + tgt_begin;
     } else {
@@ -747,6 +985,23 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     }
         PNBX_F2(1) PNBX_F2(2) PNBX_F2(3)
 #undef PNBX_F2
+    } else if (use_f2h) {
+        dim3 grid((unsigned)n_tb, (unsigned)splits);
+        const Pair8* sp = srcp.get();
+        const Vec4<float>* tp = reinterpret_cast<const Vec4<float>*>(tgt_ptr);
+        const float* th2 = self ? srch2.get() + tgt_begin : nullptr;  // at-points targets have no softening
+        const int64_t sb = self ? tgt_begin : -1;
+#define PNBX_F2H(W)                                                                                                \
+    if (want == W) {                                                                                               \
+        if (soft == SOFT_PLUMMER_PAIR)                                                                             \
+            PNBX_LAUNCH((direct_kernel_f2h<W, 1>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb,             \
+                        tiles_per_split, kp, ka);                                                                  \
+        else                                                                                                       \
+            PNBX_LAUNCH((direct_kernel_f2h<W, 2>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb,             \
+                        tiles_per_split, kp, ka);                                                                  \
+    }
+        PNBX_F2H(1) PNBX_F2H(2) PNBX_F2H(3)
+#undef PNBX_F2H
     } else {
         launch_direct<T, TILE>(want, soft, src4.get(), srch.get(), n, tgt_ptr, tgt_h_ptr, m, self ? tgt_begin : -1, eps2,
                                (int)splits, tiles_per_split, kp, ka, s);

@@ -7,6 +7,7 @@
 // pool; here host threads only ever move bytes). Pinned inputs and small arrays take the plain path.
 #include <cstring>
 #include <mutex>
+#include <system_error>
 #include <thread>
 
 #include "common.cuh"
@@ -109,11 +110,22 @@ void staged_copy(void* dev, void* host, size_t bytes, int dir, const Exec& ex) {
         PNBX_CUDA(cudaStreamWaitEvent(g_lanes[k].s, ready, 0));
     }
     cudaError_t errs[MAX_THREADS];
+    for (int k = 0; k < MAX_THREADS; ++k) errs[k] = cudaSuccess;
     std::thread th[MAX_THREADS];
-    for (int k = 0; k < nt; ++k)
-        th[k] = std::thread(lane_work, std::ref(g_lanes[k]), ex.device, k, nt, (char*)dev, (char*)host, bytes, dir, &errs[k]);
-    for (int k = 0; k < nt; ++k) th[k].join();
+    int started = 0;
+    bool spawn_failed = false;
+    for (int k = 0; k < nt; ++k) {
+        try {
+            th[k] = std::thread(lane_work, std::ref(g_lanes[k]), ex.device, k, nt, (char*)dev, (char*)host, bytes, dir, &errs[k]);
+            ++started;
+        } catch (const std::system_error&) {  // out of threads: the chunks of the missing lanes would be lost
+            spawn_failed = true;
+            break;
+        }
+    }
+    for (int k = 0; k < started; ++k) th[k].join();
     cudaEventDestroy(ready);
+    if (spawn_failed) throw ArgError{PNBX_ERR_CUDA, "staged host<->device copy: could not start the staging threads"};
     for (int k = 0; k < nt; ++k)
         if (errs[k] != cudaSuccess) throw CudaError{errs[k], "staged host<->device copy", __FILE__, __LINE__};
     // every lane drained its stream before returning: the data is in place, later work on ex.stream is ordered by
