@@ -316,7 +316,9 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
         // (+ R2_TINY of tree.rs:1117 can only matter for dist2 < 1e-300, where nothing is accepted anyway)
         const double dist2 = fma(dx, dx, fma(dy, dy, __dmul_rn(dz, dz)));
         bool accept = gm.size2 < __dmul_rn(a.theta2, dist2);
-        if (gated) accept = accept && dist2 > c.gate2 && dist2 > gate_t;  // dist2 > max(gates): node_soft_ok (tree.rs:55-71)
+        // node_soft_ok (tree.rs:55-71): dist2 > max(gates). Without an hmax payload both gates are 0 (records and gate_t),
+        // and dist2 > 0 can only fail where the opening test fails too, so softened kernels test unconditionally.
+        if (SMODE == 3 ? gated : SMODE != 0) accept = accept && dist2 > c.gate2 && dist2 > gate_t;
         accept = accept && active;
         const bool need_open = __any_sync(FULL, active && !accept);
         if (WANT == 0) {
