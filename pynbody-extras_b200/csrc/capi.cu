@@ -29,8 +29,8 @@ bool timing_enabled() {
     return on;
 }
 
-int64_t& launch_counter() {
-    static int64_t c = 0;
+std::atomic<int64_t>& launch_counter() {  // concurrent calls from several host threads are legal
+    static std::atomic<int64_t> c{0};
     return c;
 }
 KernelEvents& kernel_events() {
@@ -100,14 +100,14 @@ Exec make_exec(const pnbx_opts* opts) {
     }
     {
         // keep freed blocks in the stream-ordered pool so repeated calls never go back to cudaMalloc
-        static bool pool_set[64] = {};
-        if (dev < 64 && !pool_set[dev]) {
+        static std::atomic<bool> pool_set[64];  // zero-initialised; setting the attribute twice is harmless
+        if (dev < 64 && !pool_set[dev].load()) {
             cudaMemPool_t pool;
             if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
                 uint64_t thresh = UINT64_MAX;
                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
             }
-            pool_set[dev] = true;
+            pool_set[dev].store(true);
         }
     }
     return ex;
@@ -267,7 +267,7 @@ int pnbx_last_kernel_ms(double* ms) {
     *ms = (double)f;
     return PNBX_OK;
 }
-int64_t pnbx_launch_count(void) { return pnbx::launch_counter(); }
+int64_t pnbx_launch_count(void) { return pnbx::launch_counter().load(); }
 int pnbx_last_timings(const char** labels, double* ms, int cap) {
     auto& v = pnbx::last_times().v;
     int k = 0;

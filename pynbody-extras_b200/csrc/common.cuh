@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -166,7 +167,7 @@ struct StageTimer {
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Every kernel launch of this library goes through PNBX_LAUNCH so bench.py can report `gpu_launches`.
-int64_t& launch_counter();
+std::atomic<int64_t>& launch_counter();
 #define PNBX_LAUNCH(kernel, grid, block, smem, stream, ...)          \
     do {                                                             \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
