@@ -212,9 +212,9 @@ def tree_section(args, rank, world, local, dev, barrier, peak_tf):
             "work_model": "accepts*140(acc)|120(pot) + leaf_pairs*20 + visits*10 flop (BASELINE.md §3), counts from "
                           "pnbx_tree_walk_counters (== oracle counters)",
             "interactions_per_s": (cnt["accepts"] + cnt["leaf_particles"]) / (k_acc_ms * 1e-3),
-            "traffic": 1.473e9 if (world == 1 and n == 10_000_000) else None,
+            "traffic": 1.448e9 if (world == 1 and n == 10_000_000) else None,
             "traffic_note": "dram read+write of one N=1e7 potentials launch from ncu --set full "
-                            "(profiles/r01_walk_kernel_ncu.md, second capture); the kernel is issue bound, not HBM bound",
+                            "(profiles/r01_walk_kernel_ncu.md, final capture); the kernel is issue bound, not HBM bound",
         },
         "roofline_build": {
             "bound": "hbm", "unit": "GB/s", "achieved": 0.53e3 * n / (build_ms * 1e-3) / 1e9,
