@@ -11,6 +11,7 @@
 #pragma once
 #include <cfloat>
 #include <cstdint>
+#include <type_traits>
 
 namespace pnbx {
 namespace mp {
@@ -119,10 +120,22 @@ __host__ __device__ constexpr int lmn_index_ct(int l, int m, int n) {
 }
 __host__ __device__ constexpr bool is_pow2_small(int d) { return d == 1 || d == 2 || d == 4 || d == 8 || d == 16; }
 
+// compile-time loop: f(std::integral_constant<int, B>{}), ..., f(std::integral_constant<int, E-1>{})
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+// The loops run at COMPILE time (static_for over integral constants): every (target, source) pair is its own
+// instantiation, so exponents, signs and factorial denominators are constants, the moments stay in registers and only
+// the divisions by 6, 12, 24, ... remain as divisions. A plain `#pragma unroll` nest is too large for the compiler to
+// fold (it kept run-time loops, local-memory arrays and ~45 generic divisions per child at order 3).
 template <int ORDER, int NC>
 __device__ __forceinline__ void m2m_accumulate_ct(double (&acc)[NC], const double* __restrict__ child,
                                                   const double shift[3]) {
-    constexpr int fact[6] = {1, 1, 2, 6, 24, 120};
     double spw[3][6];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -136,32 +149,31 @@ __device__ __forceinline__ void m2m_accumulate_ct(double (&acc)[NC], const doubl
     double ch[NC];
 #pragma unroll
     for (int t = 0; t < NC; ++t) ch[t] = child[t];
-#pragma unroll
-    for (int t = 0; t < NC; ++t) {
-        const int l = kLmn[t].l, m = kLmn[t].m, n = kLmn[t].n;
-        if (l + m + n <= ORDER) {
+    static_for<0, NC>([&](auto tc) {
+        constexpr int t = decltype(tc)::value;
+        constexpr int l = kLmn[t].l, m = kLmn[t].m, n = kLmn[t].n;
+        if constexpr (l + m + n <= ORDER) {
             double sum = 0.0;
-#pragma unroll
-            for (int i = 0; i <= 5; ++i)
-#pragma unroll
-                for (int j = 0; j <= 5; ++j)
-#pragma unroll
-                    for (int k = 0; k <= 5; ++k) {
-                        if (i <= l && j <= m && k <= n) {
-                            const double base = ch[lmn_index_ct(i, j, k)];
-                            const int dl = l - i, dm = m - j, dn = n - k;
-                            // pow = sx*sy*sz (1.0 factors are exact identities), coeff = sign*pow/(dl! dm! dn!)
-                            double pw = (dl + dm + dn == 0) ? 1.0 : __dmul_rn(__dmul_rn(spw[0][dl], spw[1][dm]), spw[2][dn]);
-                            if ((dl + dm + dn) & 1) pw = -pw;
-                            const int den = fact[dl] * fact[dm] * fact[dn];
-                            const double coeff = is_pow2_small(den) ? __dmul_rn(pw, 1.0 / den) : __ddiv_rn(pw, (double)den);
-                            const double term = __dmul_rn(coeff, base);
-                            sum = (base == 0.0) ? sum : __dadd_rn(sum, term);  // the reference skips zero moments
-                        }
-                    }
+            static_for<0, l + 1>([&](auto ic) {
+                static_for<0, m + 1>([&](auto jc) {
+                    static_for<0, n + 1>([&](auto kc) {
+                        constexpr int i = decltype(ic)::value, j = decltype(jc)::value, k = decltype(kc)::value;
+                        constexpr int dl = l - i, dm = m - j, dn = n - k;
+                        constexpr int fact[6] = {1, 1, 2, 6, 24, 120};
+                        constexpr int den = fact[dl] * fact[dm] * fact[dn];
+                        const double base = ch[lmn_index_ct(i, j, k)];
+                        // pow = sx*sy*sz (1.0 factors are exact identities), coeff = sign*pow/(dl! dm! dn!)
+                        double pw = (dl + dm + dn == 0) ? 1.0 : __dmul_rn(__dmul_rn(spw[0][dl], spw[1][dm]), spw[2][dn]);
+                        if ((dl + dm + dn) & 1) pw = -pw;
+                        const double coeff = is_pow2_small(den) ? __dmul_rn(pw, 1.0 / den) : __ddiv_rn(pw, (double)den);
+                        const double term = __dmul_rn(coeff, base);
+                        sum = (base == 0.0) ? sum : __dadd_rn(sum, term);  // the reference skips zero moments
+                    });
+                });
+            });
             acc[t] = __dadd_rn(acc[t], sum);
         }
-    }
+    });
 }
 
 // ---- derivatives of 1/r and M2P ----------------------------------------------------------------
