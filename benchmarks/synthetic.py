@@ -122,6 +122,70 @@ def zoom_families(n, seed=4, dedup=False):
     return np.ascontiguousarray(pos[order]), np.ascontiguousarray(mass[order]), np.ascontiguousarray(soft[order])
 
 
+ZOOM_BLOCK = 1 << 18
+_ZOOM_FRAC = (0.5, 0.3, 0.2)          # dm / gas / star number fractions
+_ZOOM_MASS = (1.0, 0.19, 0.05)        # relative particle masses
+
+
+def zoom_range(n, lo, hi, seed=4):
+    """Particles [lo, hi) of the N-particle zoom set of config 4, generated block by block from
+    ``default_rng([seed, block])`` so that ANY rank layout reproduces the same global set (the set depends on
+    (n, seed) only, never on the world size). Same shapes as :func:`zoom_families`: dm = Hernquist core
+    (a=0.05, r<=1) + low-resolution shell 1<r<8, gas = Plummer-like a=0.1 with h ∝ local spacing, stars =
+    exponential disc; families are interleaved at random (each particle draws its family), so contiguous index
+    ranges are statistically uniform samples. Masses are normalised by the EXPECTED family counts
+    (sum ≈ 1 to ~1e-4), which keeps them independent of the realised counts of other blocks.
+    Returns pos (hi-lo,3), mass, softening, family (uint8: 0 dm, 1 gas, 2 star)."""
+    lo, hi = int(lo), int(hi)
+    assert 0 <= lo <= hi <= n
+    norm = n * sum(f * w for f, w in zip(_ZOOM_FRAC, _ZOOM_MASS))
+    h_gas_scale = 0.5 * max(_ZOOM_FRAC[1] * n, 1.0) ** (-1.0 / 3.0)
+    pos_out, mass_out, soft_out, fam_out = [], [], [], []
+    last_block = (hi - 1) // ZOOM_BLOCK if hi > lo else lo // ZOOM_BLOCK - 1
+    for b in range(lo // ZOOM_BLOCK, last_block + 1):
+        b0 = b * ZOOM_BLOCK
+        cnt = min(ZOOM_BLOCK, n - b0)
+        rng = np.random.default_rng([seed, b])
+        u = rng.random(cnt)
+        fam = np.where(u < _ZOOM_FRAC[0], 0, np.where(u < _ZOOM_FRAC[0] + _ZOOM_FRAC[1], 1, 2)).astype(np.uint8)
+        pos = np.empty((cnt, 3))
+        soft = np.empty(cnt)
+        # dm: 70 % Hernquist core, 30 % shell
+        k = np.nonzero(fam == 0)[0]
+        core = rng.random(k.shape[0]) < 0.7
+        s = np.sqrt(rng.uniform(0.0, (1.0 / 1.05) ** 2, k.shape[0]))
+        r_core = 0.05 * s / (1.0 - s)
+        r_shell = (1.0 + rng.uniform(0.0, 1.0, k.shape[0]) * (8.0 ** 3 - 1.0)) ** (1.0 / 3.0)
+        pos[k] = _isotropic(rng, np.where(core, r_core, r_shell))
+        soft[k] = 2.0e-3
+        # gas
+        k = np.nonzero(fam == 1)[0]
+        ug = rng.uniform(0.0, (1.0 + 0.1 ** 2) ** -1.5, k.shape[0])
+        rg = 0.1 / np.sqrt(np.maximum(ug, 1e-300) ** (-2.0 / 3.0) - 1.0)
+        pos[k] = _isotropic(rng, rg)
+        soft[k] = h_gas_scale * np.sqrt(rg * rg + 0.1 ** 2)
+        # stars
+        k = np.nonzero(fam == 2)[0]
+        R = np.minimum(rng.gamma(2.0, 0.02, k.shape[0]), 1.0)
+        ph = rng.uniform(0.0, 2.0 * np.pi, k.shape[0])
+        z = rng.logistic(0.0, 0.001, k.shape[0])
+        pos[k] = np.stack([R * np.cos(ph), R * np.sin(ph), z], axis=1)
+        soft[k] = 5.0e-4
+        mass = np.asarray(_ZOOM_MASS)[fam] / norm
+        a, e = max(lo, b0) - b0, min(hi, b0 + cnt) - b0
+        pos_out.append(pos[a:e]); mass_out.append(mass[a:e]); soft_out.append(soft[a:e]); fam_out.append(fam[a:e])
+    if not pos_out:
+        return np.empty((0, 3)), np.empty(0), np.empty(0), np.empty(0, np.uint8)
+    return (np.ascontiguousarray(np.concatenate(pos_out)), np.concatenate(mass_out), np.concatenate(soft_out),
+            np.concatenate(fam_out))
+
+
+def zoom_set(n, seed=4):
+    """The whole deterministic zoom set (config 4): pos, mass, softening."""
+    pos, mass, soft, _ = zoom_range(n, 0, n, seed)
+    return pos, mass, soft
+
+
 def rz_grid_targets(m, seed=5, rmin=1e-3, rmax=5.0):
     """Log-spaced (R, z) grid targets, random azimuth (config 5)."""
     rng = np.random.default_rng(seed)

@@ -43,9 +43,8 @@ struct pnbx_tree_impl {
 
     // sources, original order (owned copies, gravity.rs:154-180)
     DevBuf<double> pos, mass, h;
-    // root cube (tree.rs:628-654), host copies
-    double root_center[3] = {0, 0, 0};
-    double root_half = 0;
+    // root cube (tree.rs:628-654) on the device: {cx, cy, cz, half}
+    DevBuf<double> root4;
 
     // per particle
     DevBuf<uint64_t> key_hi, key_lo;   // original order
@@ -64,10 +63,11 @@ struct pnbx_tree_impl {
     DevBuf<uint32_t> node_start, node_count;  // particle range in sorted order (all nodes)
     DevBuf<int32_t> first_subnode, next_branch;
     DevBuf<uint64_t> path_hi, path_lo;
-    // level structure in reference ids (for bottom-up payload sweeps): ids of level d are
-    // level_ids[level_off[d] .. level_off[d+1])
+    // INTERNAL nodes grouped by level (reference ids, for the bottom-up payload sweeps): those of level d are
+    // level_ids[ilevel_off[d] .. ilevel_off[d+1]); the leaves follow behind all internal nodes
     DevBuf<int32_t> level_ids;
-    std::vector<int64_t> level_off;
+    std::vector<int64_t> ilevel_off;
+    int64_t n_internal = 0;
 
     // payloads
     DevBuf<double> nmass, ncom, hmax;  // (nn), (nn,3), (nn)

@@ -8,6 +8,7 @@
 //   K6 payloads        tree.rs:866-965, 1014-1067: mass/COM, hmax, P2M/M2M, bottom-up per level,
 //                      float64 with the reference's operation order (no FMA contraction)
 #include <cub/cub.cuh>
+#include <thrust/iterator/reverse_iterator.h>
 
 #include "multipole.cuh"
 #include "tree.cuh"
@@ -62,193 +63,265 @@ __global__ void gather_u32(const T* __restrict__ in, const uint32_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------ K5
-// BFS node arrays (struct of arrays, grown geometrically).
-struct Bfs {
-    DevBuf<uint32_t> start, count;
-    DevBuf<int32_t> parent, child_base;
-    DevBuf<uint8_t> rank, depth, nchild;
-    DevBuf<double> center, half;  // (cap,3), (cap)
-    DevBuf<uint64_t> path_hi, path_lo;
-    int64_t cap = 0, size = 0;
-    cudaStream_t s = nullptr;
+// Topology from the sorted path keys without any level-by-level host round trip.
+//
+// A cell at level L is the set of particles sharing their first L octant digits; it is a NODE of the reference's
+// tree iff it is the root or its parent cell holds more than leaf_capacity particles (tree.rs:848-851), and an
+// INTERNAL node iff it holds more than leaf_capacity itself. Populations only shrink down a path, so with
+//   b[i] = digits shared by sorted particles i-1 and i                      (b[0] = -1)
+//   D[i] = deepest level at which particle i's cell is still over-full
+//        = max over windows j in [i-cap, i] of the digits shared by particles j and j+cap   (sorted => the cap+1
+//          particles of a window all share that prefix; -1 if there is no window)
+// particle i's leaf sits at level D[i]+1, particle i starts a new leaf ("head") iff b[i] < D[i]+1, and the nodes that
+// START at a head i are exactly the levels b[i]+1 .. D[i]+1 (the last one is the leaf). Listing the heads in
+// ascending order and each head's levels in ascending order IS the depth-first pre-order of the tree, so one
+// exclusive scan numbers every node, and a single 8-byte-per-level D2H (sizes for the allocations) is the only
+// synchronisation of the build.
+constexpr int MAX_LEVELS = KEY_LEVELS + 2;  // histogram bins: levels 0 .. 43
 
-    template <class T>
-    static void grow(DevBuf<T>& b, int64_t old_elems, int64_t new_elems, cudaStream_t s) {
-        DevBuf<T> nb((size_t)new_elems, s);
-        if (old_elems) PNBX_CUDA(cudaMemcpyAsync(nb.p, b.p, (size_t)old_elems * sizeof(T), cudaMemcpyDeviceToDevice, s));
-        b = std::move(nb);
-    }
-    void reserve(int64_t want) {
-        if (want <= cap) return;
-        int64_t nc = std::max<int64_t>(want, cap + cap / 2 + 1024);
-        grow(start, size, nc, s); grow(count, size, nc, s); grow(parent, size, nc, s); grow(child_base, size, nc, s);
-        grow(rank, size, nc, s); grow(depth, size, nc, s); grow(nchild, size, nc, s);
-        grow(center, 3 * size, 3 * nc, s); grow(half, size, nc, s);
-        grow(path_hi, size, nc, s); grow(path_lo, size, nc, s);
-        cap = nc;
-    }
+__device__ __forceinline__ int shared_digits(uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo, bool two_words) {
+    const uint64_t x = ahi ^ bhi;
+    if (x) return (__clzll((long long)x) - 1) / 3;  // bit 63 is never set: digit l sits at bits 3*(21-l)+{0,1,2}
+    if (!two_words) return KEY_LEVELS_HI;
+    const uint64_t y = alo ^ blo;
+    return y ? KEY_LEVELS_HI + (__clzll((long long)y) - 1) / 3 : KEY_LEVELS;
+}
+// do sorted particles j and i share their first L digits?
+__device__ __forceinline__ bool same_prefix(const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo,
+                                            int64_t j, uint64_t ihi, uint64_t ilo, int L) {
+    if (L <= KEY_LEVELS_HI) return ((khi[j] ^ ihi) >> (63 - 3 * L)) == 0;  // L = 0: shift 63, bit 63 is clear
+    return khi[j] == ihi && ((klo[j] ^ ilo) >> (63 - 3 * (L - KEY_LEVELS_HI))) == 0;
+}
+
+// W[j] = digits shared by sorted particles j and j+cap (the over-full witness of every particle in between)
+__global__ void window_digits(const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo, int64_t nw,
+                              int64_t cap, int8_t* __restrict__ W) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nw) return;
+    W[j] = (int8_t)shared_digits(khi[j], klo ? klo[j] : 0, khi[j + cap], klo ? klo[j + cap] : 0, klo != nullptr);
+}
+struct MaxI8 {
+    __device__ __forceinline__ int8_t operator()(int8_t a, int8_t b) const { return a > b ? a : b; }
+};
+struct BlockOf {  // segment key of the van Herk sliding-window maximum: blocks of `w` consecutive windows
+    int64_t w;
+    __host__ __device__ __forceinline__ int64_t operator()(int64_t j) const { return j / w; }
+};
+struct RevBlockOf {  // the same blocks, enumerated from the end (for the suffix maxima)
+    int64_t w, last;
+    __host__ __device__ __forceinline__ int64_t operator()(int64_t r) const { return (last - r) / w; }
 };
 
-__global__ void init_root(uint32_t* start, uint32_t* count, int32_t* parent, uint8_t* rank, uint8_t* depth,
-                          double* center, double* half, uint64_t* phi, uint64_t* plo, const double* root4, uint32_t n) {
-    start[0] = 0; count[0] = n; parent[0] = -1; rank[0] = 0; depth[0] = 0;
-    center[0] = root4[0]; center[1] = root4[1]; center[2] = root4[2]; half[0] = root4[3];
-    phi[0] = 0; plo[0] = 0;
-}
-
-__device__ __forceinline__ unsigned digit_at(const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo,
-                                             uint32_t s, int level) {
-    return level <= KEY_LEVELS_HI ? (unsigned)((khi[s] >> (3 * (KEY_LEVELS_HI - level))) & 7u)
-                                  : (unsigned)((klo[s] >> (3 * (KEY_LEVELS - level))) & 7u);
-}
-
-// For every node of the current level that must split (count > leaf_capacity, tree.rs:848-851), find the 9
-// octant boundaries inside its sorted range; one thread per (node, boundary).
-__global__ void split_level(const uint32_t* __restrict__ start, const uint32_t* __restrict__ count, int64_t level_begin,
-                            int64_t level_size, int child_level, uint32_t leaf_capacity,
-                            const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo,
-                            uint32_t* __restrict__ bounds /* level_size x 9 */, uint8_t* __restrict__ nchild,
-                            int32_t* __restrict__ nchild_i32) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t j = t / 9;
-    int b = (int)(t % 9);
-    if (j >= level_size) return;
-    const uint32_t s0 = start[level_begin + j], c = count[level_begin + j];
-    if (c <= leaf_capacity) {
-        if (b == 0) { nchild[level_begin + j] = 0; nchild_i32[j] = 0; }
-        return;
-    }
-    // first position in [s0, s0+c) whose digit >= b
-    uint32_t lo = s0, hi = s0 + c;
-    if (b == 8) lo = hi;
-    else if (b > 0) {
-        while (lo < hi) {
-            uint32_t mid = lo + ((hi - lo) >> 1);
-            if (digit_at(khi, klo, mid, child_level) < (unsigned)b) lo = mid + 1;
-            else hi = mid;
+// Per sorted particle: b, D, head flag, number of nodes that start here (0 for non-heads); per-level node and
+// internal-node histograms; overflow flag if an over-full cell survives at the last key level.
+// Small capacities evaluate the windows directly; large ones read the prefix / suffix maxima (P, S) of W.
+__global__ void __launch_bounds__(256) leaf_levels(const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo,
+                                                   int64_t n, int64_t cap, int max_level,
+                                                   const int8_t* __restrict__ P, const int8_t* __restrict__ S,
+                                                   int8_t* __restrict__ b_out, int8_t* __restrict__ D_out,
+                                                   int32_t* __restrict__ nodes_here,
+                                                   unsigned long long* __restrict__ hist /* [2][MAX_LEVELS] + overflow */) {
+    __shared__ unsigned int sh[2][MAX_LEVELS];
+    for (int t = threadIdx.x; t < 2 * MAX_LEVELS; t += blockDim.x) (&sh[0][0])[t] = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool two = klo != nullptr;
+    if (i < n) {
+        const uint64_t ihi = khi[i], ilo = two ? klo[i] : 0;
+        const int b = i == 0 ? -1 : shared_digits(khi[i - 1], two ? klo[i - 1] : 0, ihi, ilo, two);
+        int D = -1;
+        const int64_t nw = n - cap;  // number of windows
+        if (nw > 0) {
+            const int64_t lo = i - cap > 0 ? i - cap : 0, hi = i < nw - 1 ? i : nw - 1;
+            if (P == nullptr) {
+                for (int64_t j = lo; j <= hi; ++j) {
+                    const int d = shared_digits(khi[j], two ? klo[j] : 0, khi[j + cap], two ? klo[j + cap] : 0, two);
+                    D = d > D ? d : D;
+                }
+            } else if (lo <= hi) {
+                const int64_t w = cap + 1;
+                if (lo / w != hi / w) D = max((int)S[lo], (int)P[hi]);
+                else D = (lo % w == 0) ? (int)P[hi] : (int)S[lo];  // same block: a clipped window at either end
+            }
+        }
+        const int leaf_level = D + 1;
+        const bool head = b < leaf_level;
+        b_out[i] = (int8_t)b;
+        D_out[i] = (int8_t)D;
+        nodes_here[i] = head ? leaf_level - b : 0;
+        if (head) {
+            if (leaf_level > max_level) atomicOr(&hist[2 * MAX_LEVELS], 1ull);
+            else {
+                for (int L = b + 1; L < leaf_level; ++L) { atomicAdd(&sh[0][L], 1u); atomicAdd(&sh[1][L], 1u); }
+                atomicAdd(&sh[0][leaf_level], 1u);
+            }
         }
     }
-    bounds[j * 9 + b] = lo;
-}
-__global__ void count_children(const uint32_t* __restrict__ count, int64_t level_begin, int64_t level_size,
-                               uint32_t leaf_capacity, const uint32_t* __restrict__ bounds, uint8_t* __restrict__ nchild,
-                               int32_t* __restrict__ nchild_i32) {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= level_size) return;
-    if (count[level_begin + j] <= leaf_capacity) return;
-    int k = 0;
-    for (int o = 0; o < 8; ++o) k += bounds[j * 9 + o + 1] > bounds[j * 9 + o];
-    nchild[level_begin + j] = (uint8_t)k;
-    nchild_i32[j] = k;
-}
-// Children in octant order, contiguous per parent (tree.rs:830-843); centre = parent +/- half/2 with the
-// reference's rounded additions.
-__global__ void emit_children(uint32_t* __restrict__ start, uint32_t* __restrict__ count, int32_t* __restrict__ parent,
-                              int32_t* __restrict__ child_base, uint8_t* __restrict__ rank, uint8_t* __restrict__ depth,
-                              const uint8_t* __restrict__ nchild, double* __restrict__ center, double* __restrict__ half,
-                              uint64_t* __restrict__ phi, uint64_t* __restrict__ plo, int64_t level_begin,
-                              int64_t level_size, int64_t next_begin, const int32_t* __restrict__ child_off,
-                              const uint32_t* __restrict__ bounds, int child_level) {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= level_size) return;
-    const int64_t p = level_begin + j;
-    if (nchild[p] == 0) { child_base[p] = -1; return; }
-    const int64_t base = next_begin + child_off[j];
-    child_base[p] = (int32_t)base;
-    const double cx = center[3 * p], cy = center[3 * p + 1], cz = center[3 * p + 2];
-    const double off = half[p] * 0.5;
-    int r = 0;
-    for (int o = 0; o < 8; ++o) {
-        const uint32_t a = bounds[j * 9 + o], b = bounds[j * 9 + o + 1];
-        if (b <= a) continue;
-        const int64_t c = base + r;
-        start[c] = a;
-        count[c] = b - a;
-        parent[c] = (int32_t)p;
-        rank[c] = (uint8_t)r;
-        depth[c] = (uint8_t)child_level;
-        center[3 * c + 0] = __dadd_rn(cx, (o & 1) ? off : -off);
-        center[3 * c + 1] = __dadd_rn(cy, (o & 2) ? off : -off);
-        center[3 * c + 2] = __dadd_rn(cz, (o & 4) ? off : -off);
-        half[c] = off;
-        uint64_t h = phi[p], l = plo[p];
-        if (child_level <= KEY_LEVELS_HI) h |= (uint64_t)o << (3 * (KEY_LEVELS_HI - child_level));
-        else l |= (uint64_t)o << (3 * (KEY_LEVELS - child_level));
-        phi[c] = h;
-        plo[c] = l;
-        ++r;
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * MAX_LEVELS; t += blockDim.x) {
+        const unsigned int v = (&sh[0][0])[t];
+        if (v) atomicAdd(&hist[t], (unsigned long long)v);
     }
 }
 
-// ---- renumbering into the reference's creation order
-__global__ void internal_flags_keys(const uint8_t* __restrict__ nchild, const uint32_t* __restrict__ start,
-                                    const uint8_t* __restrict__ depth, int64_t nn, uint8_t* __restrict__ flag,
-                                    uint64_t* __restrict__ key) {
+// Nodes in depth-first order (temporary): everything the renumbering and the final scatter need.
+struct DfsNodes {
+    uint32_t* start; uint32_t* count; uint32_t* parent; uint32_t* mask;  // mask: octants of the existing children
+    uint8_t* level; uint8_t* digit;
+    double* center; double* half; uint64_t* phi; uint64_t* plo;
+};
+// One thread per head: replays the reference's descent (tree.rs:818-838: centre +/- half/2, rounded additions) along
+// the particle's key digits and emits the nodes that start here — levels b+1 .. D+1 — with their particle ranges
+// (galloping searches in the sorted keys), their parent and their octant bit in the parent's child mask.
+__global__ void __launch_bounds__(128) emit_nodes(const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo,
+                                                  int64_t n, const int8_t* __restrict__ bq, const int8_t* __restrict__ Dq,
+                                                  const int32_t* __restrict__ nodes_here, const int32_t* __restrict__ base,
+                                                  const double* __restrict__ root4, DfsNodes d) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || nodes_here[i] == 0) return;
+    const bool two = klo != nullptr;
+    const uint64_t ihi = khi[i], ilo = two ? klo[i] : 0;
+    const int b = bq[i], leaf_level = Dq[i] + 1;
+    const int64_t id0 = base[i];  // DFS index of the node at level b+1
+    auto digit_of = [&](int L) -> unsigned {
+        return L <= KEY_LEVELS_HI ? (unsigned)((ihi >> (3 * (KEY_LEVELS_HI - L))) & 7u)
+                                  : (unsigned)((ilo >> (3 * (KEY_LEVELS - L))) & 7u);
+    };
+    // ---- particle ranges, deepest first: the leaf ends at the next head, every ancestor extends its child's range
+    int64_t e = i + 1;
+    while (e < n && nodes_here[e] == 0) ++e;
+    d.count[id0 + (leaf_level - b - 1)] = (uint32_t)(e - i);
+    for (int L = leaf_level - 1; L > b; --L) {
+        if (L == 0) e = n;
+        else if (e < n && same_prefix(khi, klo, e, ihi, ilo, L)) {
+            int64_t lo = e, step = 1, hi = e + 1;
+            while (hi < n && same_prefix(khi, klo, hi, ihi, ilo, L)) { lo = hi; step <<= 1; hi = lo + step; }
+            if (hi > n) hi = n;
+            while (hi - lo > 1) {  // invariant: lo shares the prefix, hi does not (or hi == n)
+                const int64_t mid = lo + ((hi - lo) >> 1);
+                if (same_prefix(khi, klo, mid, ihi, ilo, L)) lo = mid; else hi = mid;
+            }
+            e = hi;
+        }
+        d.count[id0 + (L - b - 1)] = (uint32_t)(e - i);
+    }
+    // ---- parent of the first node that starts here: the level-b cell around i; it starts at the first particle
+    // sharing b digits with i (i-1 does, by the definition of b)
+    uint32_t parent0 = 0xffffffffu;
+    if (i > 0) {
+        int64_t lo = i - 1, step = 1, p = lo - 1;
+        while (p >= 0 && same_prefix(khi, klo, p, ihi, ilo, b)) { lo = p; step <<= 1; p = lo - step; }
+        if (p < -1) p = -1;
+        while (lo - p > 1) {  // invariant: lo shares the prefix, p does not (or p == -1)
+            const int64_t mid = p + ((lo - p) >> 1);
+            if (same_prefix(khi, klo, mid, ihi, ilo, b)) lo = mid; else p = mid;
+        }
+        parent0 = (uint32_t)(base[lo] + (b - bq[lo] - 1));
+    }
+    // ---- geometry by the reference's descent, nodes from level b+1 on
+    double cx = root4[0], cy = root4[1], cz = root4[2], hf = root4[3];
+    for (int L = 0; L <= leaf_level; ++L) {
+        if (L > 0) {
+            const unsigned o = digit_of(L);
+            const double off = hf * 0.5;  // exact (== hf / 2.0)
+            cx = __dadd_rn(cx, (o & 1) ? off : -off);
+            cy = __dadd_rn(cy, (o & 2) ? off : -off);
+            cz = __dadd_rn(cz, (o & 4) ? off : -off);
+            hf = off;
+        }
+        if (L <= b) continue;
+        const int64_t id = id0 + (L - b - 1);
+        const unsigned o = L > 0 ? digit_of(L) : 0u;
+        const uint32_t par = L == b + 1 ? parent0 : (uint32_t)(id - 1);
+        d.start[id] = (uint32_t)i;
+        d.level[id] = (uint8_t)L;
+        d.digit[id] = (uint8_t)o;
+        d.parent[id] = par;
+        if (par != 0xffffffffu) atomicOr(&d.mask[par], 1u << o);  // integer OR: order-independent
+        d.center[3 * id] = cx; d.center[3 * id + 1] = cy; d.center[3 * id + 2] = cz;
+        d.half[id] = hf;
+        uint64_t ph = 0, pl = 0;  // octant path of the node: the particle's key truncated to L digits
+        if (L > 0) {
+            if (L <= KEY_LEVELS_HI) ph = ihi >> (63 - 3 * L) << (63 - 3 * L);
+            else { ph = ihi; pl = ilo >> (63 - 3 * (L - KEY_LEVELS_HI)) << (63 - 3 * (L - KEY_LEVELS_HI)); }
+        }
+        d.phi[id] = ph;
+        d.plo[id] = pl;
+    }
+}
+__global__ void child_counts(const uint32_t* __restrict__ mask, int64_t nn, int32_t* __restrict__ nchild) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nn) nchild[i] = __popc(mask[i]);
+}
+// Reference creation order (tree.rs:804-864): a node's children get consecutive ids when the node is subdivided,
+// before any of them is visited => id(first child of X) = 1 + (children of all internal nodes before X in depth-first
+// pre-order) = 1 + exclusive scan of the child counts in DFS order; a child's rank among its siblings is the number of
+// existing octants below its own.
+__global__ void assign_ref_ids(const uint32_t* __restrict__ parent, const uint8_t* __restrict__ digit,
+                               const uint32_t* __restrict__ mask, const int32_t* __restrict__ scan, int64_t nn,
+                               int32_t* __restrict__ ref) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nn) return;
-    flag[i] = nchild[i] > 0;
-    key[i] = ((uint64_t)start[i] << 8) | depth[i];  // DFS pre-order of internal nodes = (start, depth) ascending
-}
-__global__ void gather_nchild(const uint8_t* __restrict__ nchild, const int32_t* __restrict__ idx, int64_t ni,
-                              int32_t* __restrict__ out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ni) out[i] = nchild[idx[i]];
-}
-__global__ void scatter_first_child(const int32_t* __restrict__ idx, const int32_t* __restrict__ scan, int64_t ni,
-                                    int32_t* __restrict__ first_child_ref) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ni) first_child_ref[idx[i]] = 1 + scan[i];  // root is node 0 (tree.rs:708-709)
-}
-__global__ void assign_ref_ids(const int32_t* __restrict__ parent, const uint8_t* __restrict__ rank,
-                               const int32_t* __restrict__ first_child_ref, int64_t nn, int32_t* __restrict__ ref) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nn) return;
-    ref[i] = i == 0 ? 0 : first_child_ref[parent[i]] + rank[i];
-}
-// next_branch (tree.rs:736-776) one level at a time, in BFS indexing
-__global__ void links_level(const int32_t* __restrict__ parent, const uint8_t* __restrict__ rank,
-                            const uint8_t* __restrict__ nchild, const int32_t* __restrict__ ref, int64_t level_begin,
-                            int64_t level_size, int32_t* __restrict__ nb_bfs) {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= level_size) return;
-    const int64_t i = level_begin + j;
-    if (i == 0) { nb_bfs[0] = -1; return; }
-    const int32_t p = parent[i];
-    nb_bfs[i] = (rank[i] + 1 < nchild[p]) ? ref[i] + 1 : nb_bfs[p];
+    const uint32_t p = parent[i];
+    ref[i] = p == 0xffffffffu ? 0 : 1 + scan[p] + __popc(mask[p] & ((1u << digit[i]) - 1u));
 }
 struct FinalArrays {
     double* center; double* half; uint8_t* depth; uint32_t* start; uint32_t* count; int32_t* first_subnode;
-    int32_t* next_branch; uint64_t* path_hi; uint64_t* path_lo; uint8_t* nchild; int32_t* level_ids;
+    int32_t* next_branch; uint64_t* path_hi; uint64_t* path_lo; uint8_t* nchild;
 };
-__global__ void scatter_nodes(const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
-                              const int32_t* __restrict__ parent, const uint8_t* __restrict__ depth,
-                              const uint8_t* __restrict__ nchild, const double* __restrict__ center,
-                              const double* __restrict__ half, const uint64_t* __restrict__ phi,
-                              const uint64_t* __restrict__ plo, const int32_t* __restrict__ ref,
-                              const int32_t* __restrict__ first_child_ref, const int32_t* __restrict__ nb_bfs, int64_t nn,
-                              FinalArrays f) {
+// Scatter into the reference numbering, with the walk links of tree.rs:736-776: first_subnode = first child,
+// next_branch = next sibling, else the parent's = the first node that starts at the particle right after this node's
+// range (depth-first order), or "none" (-1) at the end of the particle list.
+__global__ void scatter_nodes(DfsNodes d, const int32_t* __restrict__ scan, const int32_t* __restrict__ ref,
+                              const int32_t* __restrict__ base, int64_t nn, int64_t n, FinalArrays f,
+                              uint8_t* __restrict__ sortkey, int32_t* __restrict__ sortval) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nn) return;
     const int32_t r = ref[i];
-    f.center[3 * r] = center[3 * i]; f.center[3 * r + 1] = center[3 * i + 1]; f.center[3 * r + 2] = center[3 * i + 2];
-    f.half[r] = half[i];
-    f.depth[r] = depth[i];
-    f.start[r] = start[i];
-    f.count[r] = count[i];
-    f.first_subnode[r] = nchild[i] > 0 ? first_child_ref[i] : -1;
-    f.next_branch[r] = nb_bfs[i];
-    f.path_hi[r] = phi[i];
-    f.path_lo[r] = plo[i];
-    f.nchild[r] = nchild[i];
-    f.level_ids[i] = r;  // BFS order is level order
+    f.center[3 * r] = d.center[3 * i]; f.center[3 * r + 1] = d.center[3 * i + 1]; f.center[3 * r + 2] = d.center[3 * i + 2];
+    f.half[r] = d.half[i];
+    f.depth[r] = d.level[i];
+    f.start[r] = d.start[i];
+    f.count[r] = d.count[i];
+    const int nc = __popc(d.mask[i]);
+    f.first_subnode[r] = nc > 0 ? 1 + scan[i] : -1;
+    const int64_t e = (int64_t)d.start[i] + d.count[i];
+    f.next_branch[r] = e < n ? ref[base[e]] : -1;
+    f.path_hi[r] = d.phi[i];
+    f.path_lo[r] = d.plo[i];
+    f.nchild[r] = (uint8_t)nc;
+    sortkey[i] = nc > 0 ? d.level[i] : (uint8_t)64;  // internal nodes grouped by level, all leaves behind them
+    sortval[i] = r;
+}
+__global__ void empty_root(const double* __restrict__ root4, FinalArrays f) {
+    f.center[0] = root4[0]; f.center[1] = root4[1]; f.center[2] = root4[2]; f.half[0] = root4[3];
+    f.depth[0] = 0; f.start[0] = 0; f.count[0] = 0; f.first_subnode[0] = -1; f.next_branch[0] = -1;
+    f.path_hi[0] = 0; f.path_lo[0] = 0; f.nchild[0] = 0;
 }
 
 // ---- leaf-internal order: ascending original index (stable bucketing, tree.rs:813-828)
-__global__ void mark_leaf_starts(const uint32_t* __restrict__ start, const uint8_t* __restrict__ nchild, int64_t nn,
-                                 uint32_t* __restrict__ flag) {
+// The key sort orders the particles of a leaf by their deeper digits; the reference keeps them in original order.
+// Leaves hold at most leaf_capacity particles: for small capacities every head sorts its own leaf in registers.
+constexpr int LEAF_SORT_MAX = 32;
+__global__ void __launch_bounds__(128) sort_leaves_small(const int32_t* __restrict__ nodes_here, int64_t n,
+                                                         uint32_t* __restrict__ perm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || nodes_here[i] == 0) return;
+    uint32_t v[LEAF_SORT_MAX];
+    int c = 0;
+    v[c++] = perm[i];
+    for (int64_t j = i + 1; j < n && c < LEAF_SORT_MAX && nodes_here[j] == 0; ++j) {  // insertion sort while loading
+        const uint32_t x = perm[j];
+        int k = c++;
+        while (k > 0 && v[k - 1] > x) { v[k] = v[k - 1]; --k; }
+        v[k] = x;
+    }
+    for (int k = 0; k < c; ++k) perm[i + k] = v[k];
+}
+// Large capacities: stable sort of the particles by leaf ordinal from the original order.
+__global__ void head_flags(const int32_t* __restrict__ nodes_here, int64_t n, uint32_t* __restrict__ flag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nn) return;
-    if (nchild[i] == 0) flag[start[i]] = 1;
+    if (i < n) flag[i] = nodes_here[i] != 0;
 }
 __global__ void leaf_ordinal_to_particles(const uint32_t* __restrict__ ord_sorted, const uint32_t* __restrict__ perm,
                                           int64_t n, uint32_t* __restrict__ ord_orig) {
@@ -587,120 +660,117 @@ void inclusive_sum_u32(const uint32_t* in, uint32_t* out, int64_t n, cudaStream_
     ++launch_counter();
 }
 
-// Builds the topology from sorted keys. Returns false if `max_level` was reached with an over-full node.
-bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const DevBuf<double>& root4, const uint64_t* skhi,
-                    const uint64_t* sklo, int max_level, StageTimer& tm) {
+// Builds the topology from sorted keys. Returns false if `max_level` was reached with an over-full cell.
+bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const double* root4, const uint64_t* skhi, const uint64_t* sklo,
+                    int max_level, StageTimer& tm) {
     const int64_t n = t.n;
-    Bfs b;
-    b.s = s;
-    b.reserve(std::max<int64_t>(1024, n / 2 + 16));
-    PNBX_LAUNCH(init_root, 1, 1, 0, s, b.start.p, b.count.p, b.parent.p, b.rank.p, b.depth.p, b.center.p, b.half.p,
-                b.path_hi.p, b.path_lo.p, root4.get(), (uint32_t)n);
-    b.size = 1;
-    std::vector<int64_t> level_off{0, 1};
-    int64_t level_begin = 0, level_size = 1;
-    int depth = 0;
-    const uint32_t cap = (uint32_t)std::min<int64_t>(t.leaf_capacity, UINT32_MAX);
-    bool overflow = false;
-    tm.begin("octree.emit_levels");
-    while (level_size > 0) {
-        if (depth == max_level) {
-            // key width exhausted: is any node left that would have to split?
-            std::vector<uint32_t> hc((size_t)level_size);
-            PNBX_CUDA(cudaMemcpyAsync(hc.data(), b.count.p + level_begin, (size_t)level_size * 4, cudaMemcpyDeviceToHost, s));
-            PNBX_CUDA(cudaStreamSynchronize(s));
-            for (uint32_t c : hc) if (c > cap) { overflow = true; break; }
-            PNBX_CUDA(cudaMemsetAsync(b.nchild.p + level_begin, 0, (size_t)level_size, s));
-            PNBX_CUDA(cudaMemsetAsync(b.child_base.p + level_begin, 0xff, (size_t)level_size * 4, s));
-            break;
-        }
-        const int child_level = depth + 1;
-        DevBuf<uint32_t> bounds((size_t)level_size * 9, s);
-        DevBuf<int32_t> nc((size_t)level_size + 1, s), off((size_t)level_size + 1, s);
-        PNBX_CUDA(cudaMemsetAsync(nc.p, 0, ((size_t)level_size + 1) * 4, s));
-        PNBX_LAUNCH(split_level, nblk(level_size * 9), 256, 0, s, b.start.p, b.count.p, level_begin, level_size,
-                    child_level, cap, skhi, sklo, bounds.p, b.nchild.p, nc.p);
-        PNBX_LAUNCH(count_children, nblk(level_size), 256, 0, s, b.count.p, level_begin, level_size, cap, bounds.p,
-                    b.nchild.p, nc.p);
-        exclusive_sum(nc.p, off.p, level_size + 1, s);
-        int32_t total = 0;
-        PNBX_CUDA(cudaMemcpyAsync(&total, off.p + level_size, 4, cudaMemcpyDeviceToHost, s));
-        PNBX_CUDA(cudaStreamSynchronize(s));
-        const int64_t next_begin = level_begin + level_size;
-        if (total > 0) b.reserve(next_begin + total);
-        PNBX_LAUNCH(emit_children, nblk(level_size), 256, 0, s, b.start.p, b.count.p, b.parent.p, b.child_base.p,
-                    b.rank.p, b.depth.p, b.nchild.p, b.center.p, b.half.p, b.path_hi.p, b.path_lo.p, level_begin,
-                    level_size, next_begin, off.p, bounds.p, child_level);
-        if (total == 0) break;
-        b.size = next_begin + total;
-        level_begin = next_begin;
-        level_size = total;
-        level_off.push_back(b.size);
-        ++depth;
+    const int64_t cap = t.leaf_capacity;
+    auto alloc_final = [&](int64_t nn) {
+        t.nn = nn;
+        t.center.alloc((size_t)3 * nn, s); t.half.alloc((size_t)nn, s); t.node_depth.alloc((size_t)nn, s);
+        t.node_start.alloc((size_t)nn, s); t.node_count.alloc((size_t)nn, s);
+        t.first_subnode.alloc((size_t)nn, s); t.next_branch.alloc((size_t)nn, s);
+        t.path_hi.alloc((size_t)nn, s); t.path_lo.alloc((size_t)nn, s);
+        t.node_nchild.alloc((size_t)nn, s);
+        return FinalArrays{t.center.p, t.half.p, t.node_depth.p, t.node_start.p, t.node_count.p, t.first_subnode.p,
+                           t.next_branch.p, t.path_hi.p, t.path_lo.p, t.node_nchild.p};
+    };
+    if (n == 0) {  // the reference's empty tree: one root leaf (tree.rs:658-734 with no points)
+        FinalArrays f = alloc_final(1);
+        PNBX_LAUNCH(empty_root, 1, 1, 0, s, root4, f);
+        t.n_leaves = 1; t.depth = 0; t.n_internal = 0;
+        t.ilevel_off.assign(2, 0);
+        t.level_ids.alloc(1, s);
+        return true;
     }
-    tm.end();
-    PNBX_CUDA(cudaGetLastError());
-    if (overflow) return false;
-
-    // ---- reference numbering
-    tm.begin("octree.renumber_links");
-    const int64_t nn = b.size;
-    DevBuf<uint8_t> flag((size_t)nn, s);
-    DevBuf<uint64_t> key((size_t)nn, s);
-    PNBX_LAUNCH(internal_flags_keys, nblk(nn), 256, 0, s, b.nchild.p, b.start.p, b.depth.p, nn, flag.p, key.p);
-    DevBuf<int32_t> int_idx((size_t)nn, s), n_sel(1, s);
-    {
+    tm.begin("octree.leaf_levels");
+    DevBuf<int8_t> bq((size_t)n, s), Dq((size_t)n, s), Pm, Sm;
+    DevBuf<int32_t> nodes_here((size_t)n, s), base((size_t)n + 1, s);
+    DevBuf<unsigned long long> hist(2 * MAX_LEVELS + 2, s);
+    PNBX_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), s));
+    const int64_t nw = n - cap;
+    if (cap > LEAF_SORT_MAX && nw > 0) {
+        // sliding-window maximum of W over windows of cap+1 entries (van Herk / Gil-Werman): prefix maxima P and
+        // suffix maxima S inside blocks of cap+1 entries; any window is covered by one S and one P entry
+        DevBuf<int8_t> W((size_t)nw, s);
+        Pm.alloc((size_t)nw, s); Sm.alloc((size_t)nw, s);
+        PNBX_LAUNCH(window_digits, nblk(nw), 256, 0, s, skhi, sklo, nw, cap, W.p);
+        cub::CountingInputIterator<int64_t> cnt(0);
+        cub::TransformInputIterator<int64_t, BlockOf, cub::CountingInputIterator<int64_t>> kf(cnt, BlockOf{cap + 1});
+        cub::TransformInputIterator<int64_t, RevBlockOf, cub::CountingInputIterator<int64_t>> kr(cnt, RevBlockOf{cap + 1, nw - 1});
         size_t bytes = 0;
-        cub::CountingInputIterator<int32_t> it(0);
-        PNBX_CUDA(cub::DeviceSelect::Flagged(nullptr, bytes, it, flag.p, int_idx.p, n_sel.p, (int)nn, s));
+        PNBX_CUDA(cub::DeviceScan::InclusiveScanByKey(nullptr, bytes, kf, W.p, Pm.p, MaxI8{}, (int)nw, cub::Equality{}, s));
         DevBuf<uint8_t> tmp(bytes, s);
-        PNBX_CUDA(cub::DeviceSelect::Flagged(tmp.get(), bytes, it, flag.p, int_idx.p, n_sel.p, (int)nn, s));
+        PNBX_CUDA(cub::DeviceScan::InclusiveScanByKey(tmp.get(), bytes, kf, W.p, Pm.p, MaxI8{}, (int)nw, cub::Equality{}, s));
+        auto rin = thrust::make_reverse_iterator(W.p + nw);
+        auto rout = thrust::make_reverse_iterator(Sm.p + nw);
+        size_t bytes2 = 0;
+        PNBX_CUDA(cub::DeviceScan::InclusiveScanByKey(nullptr, bytes2, kr, rin, rout, MaxI8{}, (int)nw, cub::Equality{}, s));
+        DevBuf<uint8_t> tmp2(bytes2, s);
+        PNBX_CUDA(cub::DeviceScan::InclusiveScanByKey(tmp2.get(), bytes2, kr, rin, rout, MaxI8{}, (int)nw, cub::Equality{}, s));
+        launch_counter() += 2;
+    }
+    PNBX_LAUNCH(leaf_levels, nblk(n), 256, 0, s, skhi, sklo, n, cap, max_level, Pm.p, Sm.p, bq.p, Dq.p, nodes_here.p, hist.p);
+    PNBX_CUDA(cudaMemsetAsync(base.p + n, 0, 4, s));
+    exclusive_sum(nodes_here.p, base.p, n, s);
+    // the one synchronisation of the build: per-level node counts (allocation sizes) and the overflow flag
+    unsigned long long hh[2 * MAX_LEVELS + 2];
+    PNBX_CUDA(cudaMemcpyAsync(hh, hist.p, sizeof(hh), cudaMemcpyDeviceToHost, s));
+    PNBX_CUDA(cudaStreamSynchronize(s));
+    tm.end();
+    if (hh[2 * MAX_LEVELS]) return false;
+    int64_t nn = 0, ni = 0;
+    int depth = 0;
+    t.ilevel_off.assign(1, 0);
+    for (int L = 0; L < MAX_LEVELS; ++L) {
+        nn += (int64_t)hh[L];
+        if (hh[L]) depth = L;
+    }
+    for (int L = 0; L <= depth; ++L) { ni += (int64_t)hh[MAX_LEVELS + L]; t.ilevel_off.push_back(ni); }
+    if (nn >= ((int64_t)1 << 31) - 16) throw ArgError{PNBX_ERR_ARG, "octree has more than 2^31 nodes"};
+
+    tm.begin("octree.emit_nodes");
+    DevBuf<uint32_t> d_start((size_t)nn, s), d_count((size_t)nn, s), d_parent((size_t)nn, s), d_mask((size_t)nn, s);
+    DevBuf<uint8_t> d_level((size_t)nn, s), d_digit((size_t)nn, s);
+    DevBuf<double> d_center((size_t)3 * nn, s), d_half((size_t)nn, s);
+    DevBuf<uint64_t> d_phi((size_t)nn, s), d_plo((size_t)nn, s);
+    PNBX_CUDA(cudaMemsetAsync(d_mask.p, 0, d_mask.bytes(), s));
+    DfsNodes d{d_start.p, d_count.p, d_parent.p, d_mask.p, d_level.p, d_digit.p, d_center.p, d_half.p, d_phi.p, d_plo.p};
+    PNBX_LAUNCH(emit_nodes, nblk(n, 128), 128, 0, s, skhi, sklo, n, bq.p, Dq.p, nodes_here.p, base.p, root4, d);
+    tm.end();
+
+    // ---- reference numbering, links, scatter
+    tm.begin("octree.renumber_links");
+    DevBuf<int32_t> nchild((size_t)nn, s), scan((size_t)nn, s), ref((size_t)nn, s), sortval((size_t)nn, s);
+    DevBuf<uint8_t> sortkey((size_t)nn, s);
+    PNBX_LAUNCH(child_counts, nblk(nn), 256, 0, s, d_mask.p, nn, nchild.p);
+    exclusive_sum(nchild.p, scan.p, nn, s);
+    PNBX_LAUNCH(assign_ref_ids, nblk(nn), 256, 0, s, d_parent.p, d_digit.p, d_mask.p, scan.p, nn, ref.p);
+    FinalArrays f = alloc_final(nn);
+    PNBX_LAUNCH(scatter_nodes, nblk(nn), 256, 0, s, d, scan.p, ref.p, base.p, nn, n, f, sortkey.p, sortval.p);
+    // internal nodes grouped by level (bottom-up payload sweeps): stable 7-bit sort of the DFS list
+    t.level_ids.alloc((size_t)nn, s);
+    {
+        DevBuf<uint8_t> key_out((size_t)nn, s);
+        size_t bytes = 0;
+        PNBX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, sortkey.p, key_out.p, sortval.p, t.level_ids.p, (int)nn, 0, 7, s));
+        DevBuf<uint8_t> tmp(bytes, s);
+        PNBX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), bytes, sortkey.p, key_out.p, sortval.p, t.level_ids.p, (int)nn, 0, 7, s));
         ++launch_counter();
     }
-    int32_t ni = 0;
-    PNBX_CUDA(cudaMemcpyAsync(&ni, n_sel.p, 4, cudaMemcpyDeviceToHost, s));
-    PNBX_CUDA(cudaStreamSynchronize(s));
-    DevBuf<int32_t> first_child_ref((size_t)nn, s), ref((size_t)nn, s), nb_bfs((size_t)nn, s);
-    PNBX_CUDA(cudaMemsetAsync(first_child_ref.p, 0xff, (size_t)nn * 4, s));
-    if (ni > 0) {
-        DevBuf<uint64_t> ikey((size_t)ni, s), ikey_s((size_t)ni, s);
-        DevBuf<uint32_t> iidx_s((size_t)ni, s);
-        PNBX_LAUNCH(gather_u32<uint64_t>, nblk(ni), 256, 0, s, key.p, (const uint32_t*)int_idx.p, (int64_t)ni, ikey.p);
-        sort_pairs<uint64_t>(ikey.p, ikey_s.p, (const uint32_t*)int_idx.p, iidx_s.p, ni, 8 + bits_for((uint64_t)t.n), s);
-        DevBuf<int32_t> ncs((size_t)ni, s), scan((size_t)ni, s);
-        PNBX_LAUNCH(gather_nchild, nblk(ni), 256, 0, s, b.nchild.p, (const int32_t*)iidx_s.p, (int64_t)ni, ncs.p);
-        exclusive_sum(ncs.p, scan.p, ni, s);
-        PNBX_LAUNCH(scatter_first_child, nblk(ni), 256, 0, s, (const int32_t*)iidx_s.p, scan.p, (int64_t)ni,
-                    first_child_ref.p);
-    }
-    PNBX_LAUNCH(assign_ref_ids, nblk(nn), 256, 0, s, b.parent.p, b.rank.p, first_child_ref.p, nn, ref.p);
-    for (size_t d = 0; d + 1 < level_off.size(); ++d) {
-        const int64_t lb = level_off[d], ls = level_off[d + 1] - lb;
-        PNBX_LAUNCH(links_level, nblk(ls), 256, 0, s, b.parent.p, b.rank.p, b.nchild.p, ref.p, lb, ls, nb_bfs.p);
-    }
-    t.nn = nn;
-    t.depth = (int)level_off.size() - 2;
-    t.level_off = level_off;
-    t.center.alloc((size_t)3 * nn, s); t.half.alloc((size_t)nn, s); t.node_depth.alloc((size_t)nn, s);
-    t.node_start.alloc((size_t)nn, s); t.node_count.alloc((size_t)nn, s);
-    t.first_subnode.alloc((size_t)nn, s); t.next_branch.alloc((size_t)nn, s);
-    t.path_hi.alloc((size_t)nn, s); t.path_lo.alloc((size_t)nn, s);
-    t.level_ids.alloc((size_t)nn, s);
-    DevBuf<uint8_t> nchild_ref((size_t)nn, s);
-    FinalArrays f{t.center.p, t.half.p, t.node_depth.p, t.node_start.p, t.node_count.p, t.first_subnode.p,
-                  t.next_branch.p, t.path_hi.p, t.path_lo.p, nchild_ref.p, t.level_ids.p};
-    PNBX_LAUNCH(scatter_nodes, nblk(nn), 256, 0, s, b.start.p, b.count.p, b.parent.p, b.depth.p, b.nchild.p, b.center.p,
-                b.half.p, b.path_hi.p, b.path_lo.p, ref.p, first_child_ref.p, nb_bfs.p, nn, f);
+    t.depth = depth;
+    t.n_internal = ni;
     t.n_leaves = nn - ni;
     tm.end();
 
-    // ---- ascending original index inside every leaf: stable sort of particles by leaf ordinal
+    // ---- ascending original index inside every leaf
     tm.begin("octree.leaf_order");
-    if (n > 0) {
+    if (cap <= LEAF_SORT_MAX) {
+        PNBX_LAUNCH(sort_leaves_small, nblk(n, 128), 128, 0, s, nodes_here.p, n, t.perm.p);
+    } else {
         DevBuf<uint32_t> lflag((size_t)n, s), lord_sorted((size_t)n, s), lord_orig((size_t)n, s), lord_out((size_t)n, s);
         DevBuf<uint32_t> iota((size_t)n, s), perm2((size_t)n, s);
-        PNBX_CUDA(cudaMemsetAsync(lflag.p, 0, (size_t)n * 4, s));
-        PNBX_LAUNCH(mark_leaf_starts, nblk(nn), 256, 0, s, b.start.p, b.nchild.p, nn, lflag.p);
+        PNBX_LAUNCH(head_flags, nblk(n), 256, 0, s, nodes_here.p, n, lflag.p);
         inclusive_sum_u32(lflag.p, lord_sorted.p, n, s);
         PNBX_LAUNCH(leaf_ordinal_to_particles, nblk(n), 256, 0, s, lord_sorted.p, t.perm.p, n, lord_orig.p);
         PNBX_LAUNCH(iota_u32, nblk(n), 256, 0, s, iota.p, n);
@@ -709,7 +779,6 @@ bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const DevBuf<double>& roo
     }
     tm.end();
     PNBX_CUDA(cudaGetLastError());
-    t.node_nchild = std::move(nchild_ref);  // child counts in reference numbering, for the payload sweeps
     return true;
 }
 
@@ -758,10 +827,10 @@ void build_mass_payload(pnbx_tree_impl& t, cudaStream_t s, StageTimer& tm) {
     a.ids = nullptr;
     a.count = nn;
     launch(true);  // every leaf of every level at once
-    for (int d = (int)t.level_off.size() - 3; d >= 0; --d) {  // the deepest level holds leaves only
-        a.ids = t.level_ids.p + t.level_off[d];
-        a.count = t.level_off[d + 1] - t.level_off[d];
-        launch(false);
+    for (int d = (int)t.ilevel_off.size() - 2; d >= 0; --d) {  // internal nodes only, deepest level first
+        a.ids = t.level_ids.p + t.ilevel_off[d];
+        a.count = t.ilevel_off[d + 1] - t.ilevel_off[d];
+        if (a.count > 0) launch(false);
     }
     t.rec.alloc((size_t)nn, s);
     PNBX_LAUNCH(build_walk_records, nblk(nn), 256, 0, s, t.nmass.p, t.ncom.p, t.half.p, t.has_hmax ? t.hmax.p : nullptr,
@@ -825,22 +894,17 @@ extern "C" int pnbx_tree_create(pnbx_tree** out, const double* pos, const double
         if (h) copy_in(t->h, h, (size_t)n);
         tm.end();
 
-        DevBuf<double> bb(6, s), root4(4, s);
+        DevBuf<double> bb(6, s);
+        t->root4.alloc(4, s);  // root cube {cx, cy, cz, half} (tree.rs:628-654); stays on the device: no host round trip
         if (n > 0) {
             tm.begin("octree.bbox");
             launch_bbox(t->pos.p, n, bb.p, s);
-            PNBX_LAUNCH(root_from_bbox, 1, 1, 0, s, bb.p, root4.p);
-            double r4[4];
-            PNBX_CUDA(cudaMemcpyAsync(r4, root4.p, sizeof(r4), cudaMemcpyDeviceToHost, s));
-            PNBX_CUDA(cudaStreamSynchronize(s));
-            for (int i = 0; i < 3; ++i) t->root_center[i] = r4[i];
-            t->root_half = r4[3];
+            PNBX_LAUNCH(root_from_bbox, 1, 1, 0, s, bb.p, t->root4.p);
             tm.end();
         } else {
             // empty point set: the reference gets a NaN-centred, half = 1e-6 root leaf of mass 0
-            double r4[4] = {0.0, 0.0, 0.0, 1e-6};
-            PNBX_CUDA(cudaMemcpyAsync(root4.p, r4, sizeof(r4), cudaMemcpyHostToDevice, s));
-            t->root_half = 1e-6;
+            static const double r4[4] = {0.0, 0.0, 0.0, 1e-6};
+            PNBX_CUDA(cudaMemcpyAsync(t->root4.p, r4, sizeof(r4), cudaMemcpyHostToDevice, s));
         }
 
         // keys + sort; first with the 21-level word only, the second word only if a level-21 cell is over-full
@@ -854,7 +918,7 @@ extern "C" int pnbx_tree_create(pnbx_tree** out, const double* pos, const double
             DevBuf<uint64_t> skhi((size_t)std::max<int64_t>(n, 1), s), sklo;
             if (n > 0) {
                 tm.begin("octree.keys_sort");
-                PNBX_LAUNCH(path_keys, nblk(n), 256, 0, s, t->pos.p, n, root4.p, levels, t->key_hi.p, t->key_lo.p);
+                PNBX_LAUNCH(path_keys, nblk(n), 256, 0, s, t->pos.p, n, t->root4.p, levels, t->key_hi.p, t->key_lo.p);
                 DevBuf<uint32_t> iota((size_t)n, s);
                 PNBX_LAUNCH(iota_u32, nblk(n), 256, 0, s, iota.p, n);
                 if (!use_lo) {
@@ -870,7 +934,7 @@ extern "C" int pnbx_tree_create(pnbx_tree** out, const double* pos, const double
                 }
                 tm.end();
             }
-            ok = build_topology(*t, s, root4, skhi.p, sklo.p, levels, tm);
+            ok = build_topology(*t, s, t->root4.p, skhi.p, sklo.p, levels, tm);
         }
         if (!ok)
             throw ArgError{PNBX_ERR_DEPTH,

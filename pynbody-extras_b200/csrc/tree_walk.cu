@@ -59,7 +59,7 @@ struct WalkArgs {
     const double* tgt;        // points: (m,3) float64
     const uint32_t* torder;   // points: walk order -> point index
     double theta2;
-    double rc[3];             // root centre (origin of the float64-mode coordinates)
+    const double* rc;         // root cube {cx,cy,cz,half} on the device (origin of the float64-mode coordinates)
     int kernel;               // PNBX_KERNEL_PLUMMER | PNBX_KERNEL_SPLINE
     double* out_pot;
     double* out_acc;
@@ -408,12 +408,12 @@ void launch_walk(int order, int want, const WalkArgs<T>& a, cudaStream_t s) {
     throw ArgError{PNBX_ERR_ARG, "internal: no walk kernel variant"};
 }
 
-__global__ void point_keys(const double* __restrict__ pos, int64_t n, double cx, double cy, double cz, double hf0,
+__global__ void point_keys(const double* __restrict__ pos, int64_t n, const double* __restrict__ root4,
                            uint64_t* __restrict__ key) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
-    double hf = hf0;
+    double cx = root4[0], cy = root4[1], cz = root4[2], hf = root4[3];
     uint64_t k = 0;
     for (int l = 1; l <= KEY_LEVELS_HI; ++l) {
         const unsigned ox = x >= cx, oy = y >= cy, oz = z >= cz;
@@ -464,8 +464,7 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         DevBuf<uint64_t> key((size_t)m, s), key_s((size_t)m, s);
         DevBuf<uint32_t> iota((size_t)m, s);
         torder.alloc((size_t)m, s);
-        PNBX_LAUNCH(point_keys, nb(m), 256, 0, s, d_tgt, m, t.root_center[0], t.root_center[1], t.root_center[2],
-                    t.root_half, key.p);
+        PNBX_LAUNCH(point_keys, nb(m), 256, 0, s, d_tgt, m, t.root4.p, key.p);
         PNBX_LAUNCH(iota32, nb(m), 256, 0, s, iota.p, m);
         size_t bytes = 0;
         PNBX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key.p, key_s.p, iota.p, torder.p, (int)m, 0, 63, s));
@@ -495,7 +494,7 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         a.cyc_block = (tree_order && ex.block_cyclic) ? ex.shard_block : 0;
         a.cyc_rank = ex.shard_rank; a.cyc_world = ex.shard_world;
         a.theta2 = theta * theta;
-        a.rc[0] = t.root_center[0]; a.rc[1] = t.root_center[1]; a.rc[2] = t.root_center[2];
+        a.rc = t.root4.p;
         a.kernel = t.kernel;
         a.out_pot = d_pot; a.out_acc = d_acc;
     };
