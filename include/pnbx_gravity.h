@@ -118,6 +118,10 @@ int pnbx_tree_create(pnbx_tree** out, const double* pos, const double* mass, con
 int pnbx_tree_build_mass(pnbx_tree* t, const double* mass);
 /* Octree.set_softenings (gravity.rs:241-258): setter only, hmax payload NOT rebuilt. */
 int pnbx_tree_set_softenings(pnbx_tree* t, const double* h);
+/* The same two calls with options: opts->mem_space = PNBX_MEM_DEVICE takes a device pointer of the tree's device,
+ * ordered after opts->stream (the caller's stream waits for the update in turn); NULL opts = host pointer. */
+int pnbx_tree_build_mass_ex(pnbx_tree* t, const double* mass, const pnbx_opts* opts);
+int pnbx_tree_set_softenings_ex(pnbx_tree* t, const double* h, const pnbx_opts* opts);
 /* Octree.set_kernel (gravity.rs:260-265). */
 int pnbx_tree_set_kernel(pnbx_tree* t, int kernel);
 /*
@@ -178,6 +182,10 @@ int64_t pnbx_shard_count(int64_t n, int64_t block, int32_t world, int32_t rank);
 /* Original particle index of every tree-order position in [begin, begin+m) (host or device int64 per opts). */
 int pnbx_tree_get_order(const pnbx_tree* t, int64_t begin, int64_t m, int64_t* out, const pnbx_opts* opts);
 /* (with PNBX_FLAG_BLOCK_CYCLIC in opts->flags: the positions of that rank's block-cyclic shard, `begin` ignored) */
+
+/* Device memory is cached by the library between calls (blocks are reused in stream order, never handed back to the
+ * driver behind the caller's back); this returns every cached block that is not in use. */
+void pnbx_trim_memory(void);
 
 /* Stage timings of the last call on this thread (GRAVITY_TIMING analogue, tree.rs:5-21):
  * fills up to `cap` (label, milliseconds) pairs, returns the count. */

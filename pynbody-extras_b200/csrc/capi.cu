@@ -1,6 +1,9 @@
 // capi.cu — error/timing state, option handling and the shared bounding-box reduction.
 #include <cfloat>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -39,16 +42,108 @@ KernelEvents& kernel_events() {
 }
 void KernelEvents::begin(cudaStream_t s) {
     if (!armed) return;
-    if (!a) {
-        cudaEventCreate(&a);
-        cudaEventCreate(&b);
+    if (!a[dev]) {  // created on the device the call runs on (make_exec selected it)
+        cudaEventCreate(&a[dev]);
+        cudaEventCreate(&b[dev]);
     }
-    cudaEventRecord(a, s);
+    cudaEventRecord(a[dev], s);
 }
 void KernelEvents::end(cudaStream_t s) {
     if (!armed) return;
-    cudaEventRecord(b, s);
+    cudaEventRecord(b[dev], s);
     valid = true;
+}
+
+// ---- library-owned caching allocator
+// Stream-ordered like cudaMallocAsync, but the cache belongs to this library (no settings of the process-wide default
+// pool are touched) and the memory is plain cudaMalloc memory, which peers can read and write once peer access is
+// enabled (multi.cu). free: the block goes to the device's free list together with an event recorded on the freeing
+// stream; alloc: best fit from the list, the allocating stream waits for that event first. Blocks are returned to the
+// driver only by pnbx_trim_memory() or when an allocation fails.
+namespace {
+struct CachedBlock {
+    void* p;
+    size_t bytes;
+    cudaEvent_t ev;  // last use, recorded at free time
+};
+struct DeviceCache {
+    std::mutex mu;
+    std::multimap<size_t, CachedBlock> free_blocks;      // by size
+    std::unordered_map<void*, CachedBlock> live;         // handed out
+};
+DeviceCache g_cache[KernelEvents::MAXDEV];
+
+size_t round_size(size_t bytes) {
+    const size_t g = bytes >= (size_t(1) << 20) ? (size_t(2) << 20) : 512;  // 2 MB granules for large blocks
+    return (bytes + g - 1) / g * g;
+}
+void trim_locked(DeviceCache& c) {
+    for (auto& kv : c.free_blocks) {
+        cudaEventSynchronize(kv.second.ev);
+        cudaFree(kv.second.p);
+        cudaEventDestroy(kv.second.ev);
+    }
+    c.free_blocks.clear();
+}
+}  // namespace
+
+void* pool_alloc(size_t bytes, cudaStream_t s) {
+    int dev = 0;
+    PNBX_CUDA(cudaGetDevice(&dev));
+    if (dev >= KernelEvents::MAXDEV) throw ArgError{PNBX_ERR_ARG, "device ordinal out of range"};
+    DeviceCache& c = g_cache[dev];
+    const size_t need = round_size(bytes ? bytes : 1);
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.free_blocks.lower_bound(need);
+    if (it != c.free_blocks.end() && it->first <= need + need / 2 + (size_t(1) << 20)) {  // do not burn a huge block on a small request
+        CachedBlock b = it->second;
+        c.free_blocks.erase(it);
+        PNBX_CUDA(cudaStreamWaitEvent(s, b.ev, 0));  // whatever used the block before has to finish first
+        c.live.emplace(b.p, b);
+        return b.p;
+    }
+    CachedBlock b{nullptr, need, nullptr};
+    cudaError_t e = cudaMalloc(&b.p, need);
+    if (e != cudaSuccess) {  // give the cache back to the driver and try once more
+        cudaGetLastError();
+        trim_locked(c);
+        e = cudaMalloc(&b.p, need);
+    }
+    if (e != cudaSuccess) throw CudaError{e, "cudaMalloc (library cache)", __FILE__, __LINE__};
+    PNBX_CUDA(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming));
+    c.live.emplace(b.p, b);
+    return b.p;
+}
+void pool_free(void* p, cudaStream_t s) {
+    if (!p) return;
+    cudaPointerAttributes at;
+    int dev = 0;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess) dev = at.device;
+    else cudaGetLastError();
+    DeviceCache& c = g_cache[dev < KernelEvents::MAXDEV ? dev : 0];
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) return;  // not ours
+    CachedBlock b = it->second;
+    c.live.erase(it);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != dev) cudaSetDevice(dev);  // the event belongs to the block's device
+    cudaEventRecord(b.ev, s);
+    if (cur != dev) cudaSetDevice(cur);
+    c.free_blocks.emplace(b.bytes, b);
+}
+void pool_trim() {
+    for (auto& c : g_cache) {
+        std::lock_guard<std::mutex> lock(c.mu);
+        if (c.free_blocks.empty()) continue;
+        cudaPointerAttributes at;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cudaPointerGetAttributes(&at, c.free_blocks.begin()->second.p) == cudaSuccess) cudaSetDevice(at.device);
+        trim_locked(c);
+        cudaSetDevice(cur);
+    }
 }
 
 int fail(int code, const std::string& msg) {
@@ -83,7 +178,7 @@ Exec make_exec(const pnbx_opts* opts) {
             throw ArgError{PNBX_ERR_ARG, "bad shard_rank / shard_world"};
     }
     kernel_events().armed = ex.kernel_events;
-    if (ex.kernel_events) kernel_events().valid = false;
+    if (ex.kernel_events) { kernel_events().valid = false; kernel_events().dev = dev < KernelEvents::MAXDEV ? dev : 0; }
     if (opts && (opts->stream || ex.device_ptrs)) {
         // device pointers are ordered against the caller's stream: NULL means the CUDA default stream
         ex.stream = (cudaStream_t)opts->stream;
@@ -96,18 +191,6 @@ Exec make_exec(const pnbx_opts* opts) {
         } else {
             PNBX_CUDA(cudaStreamCreateWithFlags(&ex.stream, cudaStreamNonBlocking));
             ex.own_stream = true;
-        }
-    }
-    {
-        // keep freed blocks in the stream-ordered pool so repeated calls never go back to cudaMalloc
-        static std::atomic<bool> pool_set[64];  // zero-initialised; setting the attribute twice is harmless
-        if (dev < 64 && !pool_set[dev].load()) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                uint64_t thresh = UINT64_MAX;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
-            }
-            pool_set[dev].store(true);
         }
     }
     return ex;
@@ -261,13 +344,14 @@ int64_t pnbx_shard_count(int64_t n, int64_t block, int32_t world, int32_t rank) 
 int pnbx_last_kernel_ms(double* ms) {
     auto& k = pnbx::kernel_events();
     if (!k.valid || !ms) return pnbx::fail(PNBX_ERR_STATE, "no kernel events recorded (PNBX_FLAG_KERNEL_EVENTS not set)");
-    if (cudaEventSynchronize(k.b) != cudaSuccess) return pnbx::fail(PNBX_ERR_CUDA, "cudaEventSynchronize failed");
+    if (cudaEventSynchronize(k.b[k.dev]) != cudaSuccess) return pnbx::fail(PNBX_ERR_CUDA, "cudaEventSynchronize failed");
     float f = 0.f;
-    if (cudaEventElapsedTime(&f, k.a, k.b) != cudaSuccess) return pnbx::fail(PNBX_ERR_CUDA, "cudaEventElapsedTime failed");
+    if (cudaEventElapsedTime(&f, k.a[k.dev], k.b[k.dev]) != cudaSuccess) return pnbx::fail(PNBX_ERR_CUDA, "cudaEventElapsedTime failed");
     *ms = (double)f;
     return PNBX_OK;
 }
 int64_t pnbx_launch_count(void) { return pnbx::launch_counter().load(); }
+void pnbx_trim_memory(void) { pnbx::pool_trim(); }
 int pnbx_last_timings(const char** labels, double* ms, int cap) {
     auto& v = pnbx::last_times().v;
     int k = 0;

@@ -40,6 +40,16 @@ constexpr int TILE64 = 256; // sources per stage, fp64 verification path (8 KB o
 
 enum Soft { SOFT_NEWTON = 0, SOFT_PLUMMER_CONST = 1, SOFT_PLUMMER_PAIR = 2, SOFT_SPLINE = 3 };
 
+// Which kernel variant a call needs depends on the DATA (are the softenings / masses constant? is one negative?).
+// That is decided on the device (classify_direct) and every candidate variant is launched with a gate: the ones that
+// were not chosen return at once. No host round trip, so device-pointer calls stay purely stream-ordered.
+enum Variant { V_F2_CONSTM = 0, V_F2 = 1, V_F2H = 2, V_SCALAR_CONST = 3, V_SCALAR_PAIR = 4 };
+struct DirectPlan {
+    int variant;
+    float eps2_f, mass_f;
+    double eps2_d, mass_d;
+};
+
 template <class T>
 struct alignas(sizeof(T) * 4) Vec4 {
     T x, y, z, w;
@@ -214,8 +224,11 @@ template <int WANT, int SOFT, class T, int TILE>
 __global__ void __launch_bounds__(DT, PNBX_MINB)
 direct_kernel(const Vec4<T>* __restrict__ src, const T* __restrict__ src_h, int64_t n_src,
               const Vec4<T>* __restrict__ tgt, const T* __restrict__ tgt_h, int64_t m, int64_t self_base,
-              T eps2_const, int tiles_per_split, double* __restrict__ out_pot, double* __restrict__ out_acc) {
+              const DirectPlan* __restrict__ plan, int my_variant, int tiles_per_split, double* __restrict__ out_pot,
+              double* __restrict__ out_acc) {
     constexpr bool PAIR_H = (SOFT == SOFT_PLUMMER_PAIR || SOFT == SOFT_SPLINE);
+    if (plan->variant != my_variant) return;  // not the variant this call's data needs (whole grid, before any barrier)
+    const T eps2_const = sizeof(T) == 4 ? (T)plan->eps2_f : (T)plan->eps2_d;
     __shared__ Vec4<T> s_src[STAGES][TILE];
     __shared__ alignas(16) T s_h[PAIR_H ? STAGES : 1][PAIR_H ? TILE : 4];
     __shared__ alignas(8) uint64_t s_full[STAGES];
@@ -382,9 +395,11 @@ constexpr int TILEP = TILE32 / 2;  // pair records per stage
 template <int WANT, bool CONSTM>
 __global__ void __launch_bounds__(DT, PNBX_MINB)
 direct_kernel_f2(const Pair8* __restrict__ src, int64_t n_src, const Vec4<float>* __restrict__ tgt, int64_t m,
-                 int64_t self_base, float eps2_const, float mass_const, int tiles_per_split,
+                 int64_t self_base, const DirectPlan* __restrict__ plan, int tiles_per_split,
                  double* __restrict__ out_pot, double* __restrict__ out_acc) {
     __shared__ Pair8 s_src[STAGES][TILEP];
+    if (plan->variant != (CONSTM ? V_F2_CONSTM : V_F2)) return;
+    const float eps2_const = plan->eps2_f;
     __shared__ alignas(8) uint64_t s_full[STAGES];
     const int tid = threadIdx.x;
     const int64_t n_pairs = (n_src + 1) / 2;  // the odd tail is padded by pack_pairs (zero mass, far away)
@@ -503,7 +518,7 @@ direct_kernel_f2(const Pair8* __restrict__ src, int64_t n_src, const Vec4<float>
         __syncthreads();
     }
     const int64_t split_off = (int64_t)blockIdx.y * m;
-    const double ms = CONSTM ? (double)mass_const : 1.0;
+    const double ms = CONSTM ? plan->mass_d : 1.0;
 #pragma unroll
     for (int k = 0; k < TPT; ++k) {
         int64_t i = tgt_base + k * DT + tid;
@@ -565,8 +580,10 @@ template <int WANT, int HMODE>
 __global__ void __launch_bounds__(DT, PNBX_MINB)
 direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h2, int64_t n_src,
                   const Vec4<float>* __restrict__ tgt, const float* __restrict__ tgt_h2, int64_t m, int64_t self_base,
-                  int tiles_per_split, double* __restrict__ out_pot, double* __restrict__ out_acc) {
+                  const DirectPlan* __restrict__ plan, int tiles_per_split, double* __restrict__ out_pot,
+                  double* __restrict__ out_acc) {
     __shared__ Pair8 s_src[STAGES][TILEP];
+    if (plan->variant != V_F2H) return;
     __shared__ alignas(16) float2 s_h2[STAGES][TILEP];
     __shared__ alignas(8) uint64_t s_full[STAGES];
     const int tid = threadIdx.x;
@@ -816,33 +833,69 @@ __global__ void minmax_scalar_blocks(const double* __restrict__ in, int64_t n, d
     }
     if (threadIdx.x == 0) { part[2 * blockIdx.x] = smn[0]; part[2 * blockIdx.x + 1] = smx[0]; }
 }
-__global__ void minmax_pairs_final(const double* __restrict__ part, int nparts, double* __restrict__ out2) {
-    double mn = INFINITY, mx = -INFINITY;
-    for (int i = 0; i < nparts; ++i) { mn = fmin(mn, part[2 * i]); mx = fmax(mx, part[2 * i + 1]); }
-    out2[0] = mn;
-    out2[1] = mx;
+// Final min/max of the softenings and masses, then the variant decision (mirrors the case analysis of direct.rs /
+// kernel.rs; see run_direct). One thread.
+struct ClassifyArgs {
+    const double* hpart; const double* mpart; int nparts;  // partial min/max pairs (nullable)
+    int kernel, self, packed, allow_f2h, allow_constm;
+};
+__global__ void classify_direct(ClassifyArgs c, DirectPlan* __restrict__ plan) {
+    double hmn = 0.0, hmx = 0.0, mmn = 1.0, mmx = 1.0;
+    if (c.hpart) {
+        hmn = INFINITY; hmx = -INFINITY;
+        for (int i = 0; i < c.nparts; ++i) { hmn = fmin(hmn, c.hpart[2 * i]); hmx = fmax(hmx, c.hpart[2 * i + 1]); }
+    }
+    if (c.mpart) {
+        mmn = INFINITY; mmx = -INFINITY;
+        for (int i = 0; i < c.nparts; ++i) { mmn = fmin(mmn, c.mpart[2 * i]); mmx = fmax(mmx, c.mpart[2 * i + 1]); }
+    }
+    DirectPlan p;
+    double he2 = 0.0;   // constant Plummer softening squared
+    bool pair = false;  // per-pair softening h = max(h_i, h_j) needed
+    const bool constant = hmn == hmx;
+    if (c.kernel == PNBX_KERNEL_PLUMMER && c.hpart) {
+        // constant h: self max(h,h) = h; points max(h,0). Negative constant: |h| in self mode (h*h), Newtonian at
+        // points (direct.rs:560) — both equal he^2 below.
+        if (constant) { const double he = c.self ? hmn : fmax(hmn, 0.0); he2 = he * he; }
+        else pair = true;
+    } else if (c.kernel == PNBX_KERNEL_SPLINE && c.hpart) {
+        pair = !(constant && hmn <= 0.0);  // spline with h <= 0 is Newtonian (kernel.rs:46-48)
+    }
+    p.eps2_f = (float)he2 + FLT_MIN;  // + the reference's R2_TINY
+    p.eps2_d = he2 + DBL_MIN;
+    p.mass_d = mmn;
+    p.mass_f = (float)mmn;
+    if (!pair) {
+        p.variant = !c.packed ? V_SCALAR_CONST : (c.allow_constm && mmn == mmx) ? V_F2_CONSTM : V_F2;
+    } else {
+        // packed per-pair path: needs h^2 = max(h_i^2, h_j^2), i.e. every softening that takes part >= 0. The spline
+        // clamps at 0 anyway (h <= 0 is Newtonian), at-points Plummer uses max(h_j, 0) (direct.rs:560); Plummer in
+        // self mode with a negative softening (max(h_i, h_j) of signed values) stays on the scalar kernel.
+        const bool f2h_ok = c.packed && c.allow_f2h && (c.kernel == PNBX_KERNEL_SPLINE || !c.self || hmn >= 0.0);
+        p.variant = f2h_ok ? V_F2H : V_SCALAR_PAIR;
+    }
+    *plan = p;
 }
 
 template <int WANT, int SOFT, class T, int TILE>
 void launch_direct_t(const Vec4<T>* src, const T* src_h, int64_t n, const Vec4<T>* tgt, const T* tgt_h, int64_t m,
-                     int64_t self_base, T eps2, int splits, int tiles_per_split, double* pot, double* acc,
-                     cudaStream_t s) {
+                     int64_t self_base, const DirectPlan* plan, int variant, int splits, int tiles_per_split, double* pot,
+                     double* acc, cudaStream_t s) {
     dim3 grid((unsigned)ceil_div(m, DT * TPT), (unsigned)splits);
-    PNBX_LAUNCH((direct_kernel<WANT, SOFT, T, TILE>), grid, DT, 0, s, src, src_h, n, tgt, tgt_h, m, self_base, eps2,
+    PNBX_LAUNCH((direct_kernel<WANT, SOFT, T, TILE>), grid, DT, 0, s, src, src_h, n, tgt, tgt_h, m, self_base, plan, variant,
                 tiles_per_split, pot, acc);
 }
 
 template <class T, int TILE>
 void launch_direct(int want, int soft, const Vec4<T>* src, const T* src_h, int64_t n, const Vec4<T>* tgt,
-                   const T* tgt_h, int64_t m, int64_t self_base, T eps2, int splits, int tiles_per_split,
-                   double* pot, double* acc, cudaStream_t s) {
+                   const T* tgt_h, int64_t m, int64_t self_base, const DirectPlan* plan, int variant, int splits,
+                   int tiles_per_split, double* pot, double* acc, cudaStream_t s) {
 #define PNBX_CASE(W, S)                                                                                          \
     if (want == W && soft == S) {                                                                                \
-        launch_direct_t<W, S, T, TILE>(src, src_h, n, tgt, tgt_h, m, self_base, eps2, splits, tiles_per_split,  \
-                                       pot, acc, s);                                                             \
+        launch_direct_t<W, S, T, TILE>(src, src_h, n, tgt, tgt_h, m, self_base, plan, variant, splits,          \
+                                       tiles_per_split, pot, acc, s);                                            \
         return;                                                                                                  \
     }
-    PNBX_CASE(1, SOFT_NEWTON) PNBX_CASE(2, SOFT_NEWTON) PNBX_CASE(3, SOFT_NEWTON)
     PNBX_CASE(1, SOFT_PLUMMER_CONST) PNBX_CASE(2, SOFT_PLUMMER_CONST) PNBX_CASE(3, SOFT_PLUMMER_CONST)
     PNBX_CASE(1, SOFT_PLUMMER_PAIR) PNBX_CASE(2, SOFT_PLUMMER_PAIR) PNBX_CASE(3, SOFT_PLUMMER_PAIR)
     PNBX_CASE(1, SOFT_SPLINE) PNBX_CASE(2, SOFT_SPLINE) PNBX_CASE(3, SOFT_SPLINE)
@@ -856,96 +909,68 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
                 double* d_acc, StageTimer& tm) {
     cudaStream_t s = ex.stream;
     const bool self = d_tgt == nullptr;
+    constexpr int NPART = 296;
 
     tm.begin("direct.pack");
     DevBuf<double> bbox(6, s);
     launch_bbox(d_pos, n, bbox.get(), s);
 
-    // softening mode
-    int soft = SOFT_NEWTON;
-    T eps2 = sizeof(T) == 4 ? (T)FLT_MIN : (T)DBL_MIN;  // the reference's + R2_TINY
-    bool pair_h = false;
-    double hmm[2] = {0.0, 0.0};  // min / max of the source softenings
-    if (kernel == PNBX_KERNEL_PLUMMER || kernel == PNBX_KERNEL_SPLINE) {
-        if (d_h) {
-            DevBuf<double> part(2 * 296, s), res(2, s);
-            PNBX_LAUNCH(minmax_scalar_blocks, 296, 256, 0, s, d_h, n, part.get());
-            PNBX_LAUNCH(minmax_pairs_final, 1, 1, 0, s, part.get(), 296, res.get());
-            PNBX_CUDA(cudaMemcpyAsync(hmm, res.get(), sizeof(hmm), cudaMemcpyDeviceToHost, s));
-            PNBX_CUDA(cudaStreamSynchronize(s));
-        }
-        const bool constant = hmm[0] == hmm[1];
-        if (kernel == PNBX_KERNEL_PLUMMER) {
-            // constant h: self max(h,h) = h; points max(h,0). Negative constant: |h| in self mode (h*h),
-            // Newtonian at points (direct.rs:560) — both equal h_eff^2 below.
-            if (constant) {
-                double he = self ? hmm[0] : std::max(hmm[0], 0.0);
-                soft = SOFT_PLUMMER_CONST;
-                eps2 = (T)(he * he) + eps2;
-            } else {
-                soft = SOFT_PLUMMER_PAIR;
-                pair_h = true;
-            }
-        } else {
-            if (constant && hmm[0] <= 0.0) soft = SOFT_NEWTON;  // spline with h<=0 is Newtonian (kernel.rs:46-48)
-            else { soft = SOFT_SPLINE; pair_h = true; }
-        }
+    // ---- variant decision on the device
+    const bool soft_kernel = kernel == PNBX_KERNEL_PLUMMER || kernel == PNBX_KERNEL_SPLINE;
+    const bool have_h = soft_kernel && d_h != nullptr;
+    const bool packed = sizeof(T) == 4 && !getenv("PNBX_DIRECT_SCALAR");  // packed FFMA2 kernels (fp32 only)
+    const bool allow_f2h = !getenv("PNBX_DIRECT_NO_F2H");
+    const bool allow_constm = !getenv("PNBX_DIRECT_NO_CONSTM");
+    DevBuf<double> hpart, mpart;
+    DevBuf<DirectPlan> plan(1, s);
+    if (have_h) {
+        hpart.alloc(2 * NPART, s);
+        PNBX_LAUNCH(minmax_scalar_blocks, NPART, 256, 0, s, d_h, n, hpart.get());
     }
+    const bool check_mass = packed && allow_constm && d_mass != nullptr;  // unit masses are constant (direct.rs:121-128)
+    if (check_mass) {
+        mpart.alloc(2 * NPART, s);
+        PNBX_LAUNCH(minmax_scalar_blocks, NPART, 256, 0, s, d_mass, n, mpart.get());
+    }
+    ClassifyArgs ca{hpart.get(), mpart.get(), NPART, kernel, self ? 1 : 0, packed ? 1 : 0, allow_f2h ? 1 : 0,
+                    allow_constm ? 1 : 0};
+    PNBX_LAUNCH(classify_direct, 1, 1, 0, s, ca, plan.get());
+    // which variants can the decision come out as? (everything the host can rule out is not even launched)
+    const bool may_const = true;                                   // constant / absent softening
+    const bool may_pair = have_h;                                  // per-pair softening
+    const bool may_f2_constm = packed && may_const && allow_constm;
+    const bool may_f2 = packed && may_const && (d_mass != nullptr || !allow_constm);
+    const bool may_f2h = packed && may_pair && allow_f2h;
+    const bool may_scalar_const = !packed;
+    const bool may_scalar_pair = may_pair && (!packed || !allow_f2h || (kernel == PNBX_KERNEL_PLUMMER && self));
 
-    const bool f2_ok = sizeof(T) == 4 && !getenv("PNBX_DIRECT_SCALAR");
-    const bool use_f2 = f2_ok && !pair_h;  // packed FFMA2 path, constant softening
-    // packed per-pair path: needs h^2 = max(h_i^2, h_j^2), i.e. every softening that takes part >= 0. The spline clamps
-    // at 0 anyway (h <= 0 is Newtonian), at-points Plummer uses max(h_j, 0) (direct.rs:560); Plummer in self mode with a
-    // negative softening (max(h_i, h_j) of signed values) stays on the scalar kernel.
-    const bool use_f2h = f2_ok && pair_h && !getenv("PNBX_DIRECT_NO_F2H") &&
-                         (soft == SOFT_SPLINE || !self || hmm[0] >= 0.0);
-    bool const_mass = false;
-    double mass_value = 1.0;
-    if (use_f2 && !getenv("PNBX_DIRECT_NO_CONSTM")) {
-        if (!d_mass) const_mass = true;  // unit masses (direct.rs:121-128)
-        else {
-            double mm[2];
-            DevBuf<double> part(2 * 296, s), res(2, s);
-            PNBX_LAUNCH(minmax_scalar_blocks, 296, 256, 0, s, d_mass, n, part.get());
-            PNBX_LAUNCH(minmax_pairs_final, 1, 1, 0, s, part.get(), 296, res.get());
-            PNBX_CUDA(cudaMemcpyAsync(mm, res.get(), sizeof(mm), cudaMemcpyDeviceToHost, s));
-            PNBX_CUDA(cudaStreamSynchronize(s));
-            const_mass = mm[0] == mm[1];
-            mass_value = mm[0];
-        }
-    }
+    // ---- packing
     DevBuf<Vec4<T>> src4;
     DevBuf<Pair8> srcp;
     DevBuf<float> srch2;
-    if (use_f2 || use_f2h) {
+    DevBuf<T> srch;
+    if (packed) {
         srcp.alloc((size_t)(n + 1) / 2, s);
         PNBX_LAUNCH(pack_pairs, (unsigned)ceil_div((n + 1) / 2, 256), 256, 0, s, d_pos, d_mass, n, bbox.get(), srcp.get());
-        if (use_f2h) {
+        if (may_f2h) {
             const int64_t np = ((n + 1) / 2) * 2 + 4;  // whole pair records + room for the 16-byte rounding of the bulk copy
             srch2.alloc((size_t)np, s);
             PNBX_LAUNCH(pack_h2, (unsigned)ceil_div(np, 256), 256, 0, s, d_h, n, np, srch2.get());
         }
-    } else {
+    }
+    if (may_scalar_const || may_scalar_pair) {
         src4.alloc((size_t)n, s);
         PNBX_LAUNCH(pack_points<T>, (unsigned)ceil_div(n, 256), 256, 0, s, d_pos, d_mass, n, bbox.get(), T(1), src4.get());
+        if (may_scalar_pair) {
+            int64_t np = ceil_div(n, 4) * 4 + 4;  // padded to 16 B granules for the bulk copy
+            srch.alloc((size_t)np, s);
+            PNBX_LAUNCH(pack_scalar<T>, (unsigned)ceil_div(np, 256), 256, 0, s, d_h, n, np, kernel == PNBX_KERNEL_SPLINE, srch.get());
+        }
     }
-    DevBuf<T> srch;
-    if (pair_h && !use_f2h) {
-        int64_t np = ceil_div(n, 4) * 4 + 4;  // padded to 16 B granules for the bulk copy
-        srch.alloc((size_t)np, s);
-        PNBX_LAUNCH(pack_scalar<T>, (unsigned)ceil_div(np, 256), 256, 0, s, d_h, n, np, soft == SOFT_SPLINE, srch.get());
-    }
-    DevBuf<Vec4<T>> tgt4;
-    const Vec4<T>* tgt_ptr;
-    const T* tgt_h_ptr = nullptr;
-    if (self && !use_f2 && !use_f2h) {
-        tgt_ptr = src4.get() + tgt_begin;
-        if (pair_h) tgt_h_ptr = srch.get() + tgt_begin;
-    } else {
-        tgt4.alloc((size_t)m, s);
+    DevBuf<Vec4<T>> tgt4((size_t)m, s);
+    {
         const double* tp = self ? d_pos + 3 * tgt_begin : d_tgt;
         PNBX_LAUNCH(pack_points<T>, (unsigned)ceil_div(m, 256), 256, 0, s, tp, nullptr, m, bbox.get(), T(0), tgt4.get());
-        tgt_ptr = tgt4.get();
     }
     PNBX_CUDA(cudaGetLastError());
     tm.end();
@@ -969,43 +994,34 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     }
     tm.begin("direct.kernel");
     kernel_events().begin(s);
-    if (use_f2) {
-        dim3 grid((unsigned)n_tb, (unsigned)splits);
+    const int64_t sb = self ? tgt_begin : -1;
+    dim3 grid((unsigned)n_tb, (unsigned)splits);
+    if constexpr (sizeof(T) == 4) {
         const Pair8* sp = srcp.get();
-        const Vec4<float>* tp = reinterpret_cast<const Vec4<float>*>(tgt_ptr);
-        const int64_t sb = self ? tgt_begin : -1;
-#define PNBX_F2(W)                                                                                                 \
-    if (want == W) {                                                                                               \
-        if (const_mass)                                                                                            \
-            PNBX_LAUNCH((direct_kernel_f2<W, true>), grid, DT, 0, s, sp, n, tp, m, sb, (float)eps2, (float)mass_value,  \
-                        tiles_per_split, kp, ka);                                                                  \
-        else                                                                                                       \
-            PNBX_LAUNCH((direct_kernel_f2<W, false>), grid, DT, 0, s, sp, n, tp, m, sb, (float)eps2, 1.f,          \
-                        tiles_per_split, kp, ka);                                                                  \
+        const Vec4<float>* tp = reinterpret_cast<const Vec4<float>*>(tgt4.get());
+        const DirectPlan* pl = plan.get();
+#define PNBX_F2(W)                                                                                                     \
+    if (want == W) {                                                                                                   \
+        if (may_f2_constm) PNBX_LAUNCH((direct_kernel_f2<W, true>), grid, DT, 0, s, sp, n, tp, m, sb, pl, tiles_per_split, kp, ka);  \
+        if (may_f2) PNBX_LAUNCH((direct_kernel_f2<W, false>), grid, DT, 0, s, sp, n, tp, m, sb, pl, tiles_per_split, kp, ka);        \
+        if (may_f2h) {                                                                                                 \
+            const float* th2 = self ? srch2.get() + tgt_begin : nullptr; /* at-points targets have no softening */    \
+            if (kernel == PNBX_KERNEL_PLUMMER)                                                                         \
+                PNBX_LAUNCH((direct_kernel_f2h<W, 1>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
+            else                                                                                                       \
+                PNBX_LAUNCH((direct_kernel_f2h<W, 2>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
+        }                                                                                                              \
     }
         PNBX_F2(1) PNBX_F2(2) PNBX_F2(3)
 #undef PNBX_F2
-    } else if (use_f2h) {
-        dim3 grid((unsigned)n_tb, (unsigned)splits);
-        const Pair8* sp = srcp.get();
-        const Vec4<float>* tp = reinterpret_cast<const Vec4<float>*>(tgt_ptr);
-        const float* th2 = self ? srch2.get() + tgt_begin : nullptr;  // at-points targets have no softening
-        const int64_t sb = self ? tgt_begin : -1;
-#define PNBX_F2H(W)                                                                                                \
-    if (want == W) {                                                                                               \
-        if (soft == SOFT_PLUMMER_PAIR)                                                                             \
-            PNBX_LAUNCH((direct_kernel_f2h<W, 1>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb,             \
-                        tiles_per_split, kp, ka);                                                                  \
-        else                                                                                                       \
-            PNBX_LAUNCH((direct_kernel_f2h<W, 2>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb,             \
-                        tiles_per_split, kp, ka);                                                                  \
     }
-        PNBX_F2H(1) PNBX_F2H(2) PNBX_F2H(3)
-#undef PNBX_F2H
-    } else {
-        launch_direct<T, TILE>(want, soft, src4.get(), srch.get(), n, tgt_ptr, tgt_h_ptr, m, self ? tgt_begin : -1, eps2,
+    if (may_scalar_const)
+        launch_direct<T, TILE>(want, SOFT_PLUMMER_CONST, src4.get(), nullptr, n, tgt4.get(), nullptr, m, sb, plan.get(),
+                               V_SCALAR_CONST, (int)splits, tiles_per_split, kp, ka, s);
+    if (may_scalar_pair)
+        launch_direct<T, TILE>(want, kernel == PNBX_KERNEL_SPLINE ? SOFT_SPLINE : SOFT_PLUMMER_PAIR, src4.get(), srch.get(), n,
+                               tgt4.get(), self ? srch.get() + tgt_begin : nullptr, m, sb, plan.get(), V_SCALAR_PAIR,
                                (int)splits, tiles_per_split, kp, ka, s);
-    }
     kernel_events().end(s);
     PNBX_CUDA(cudaGetLastError());
     if (splits > 1) {
@@ -1019,6 +1035,16 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
 }
 
 }  // namespace
+
+// Direct sum on ONE device with device-resident float64 inputs: the body of pnbx_direct, also run per device by the
+// multi-device path (multi.cu). Stream-ordered on ex.stream, no host synchronisation.
+void direct_on_device(const Exec& ex, const double* d_pos, const double* d_mass, const double* d_h, int64_t n,
+                      const double* d_tgt, int64_t m, int64_t tgt_begin, int kernel, int want, double* d_pot,
+                      double* d_acc, StageTimer& tm) {
+    if (ex.f64) run_direct<double, TILE64>(ex, d_pos, d_mass, d_h, n, d_tgt, m, tgt_begin, kernel, want, d_pot, d_acc, tm);
+    else run_direct<float, TILE32>(ex, d_pos, d_mass, d_h, n, d_tgt, m, tgt_begin, kernel, want, d_pot, d_acc, tm);
+}
+
 }  // namespace pnbx
 
 extern "C" int pnbx_direct(const double* src_pos, const double* src_mass, const double* src_h, int64_t n,
@@ -1039,6 +1065,11 @@ extern "C" int pnbx_direct(const double* src_pos, const double* src_mass, const 
         if (self && (tgt_begin < 0 || tgt_begin + m > n)) throw ArgError{PNBX_ERR_ARG, "target shard outside [0, N)"};
         if (n >= (int64_t)1 << 31 || m >= (int64_t)1 << 40) throw ArgError{PNBX_ERR_ARG, "problem too large"};
 
+        // PNBX_DEVICES: whole-array host call without an explicit device -> all listed GPUs (multi.cu)
+        if (n > 0 && m > 0 && tgt_begin == 0 && (!self || m == n) &&
+            (!opts || (opts->mem_space == PNBX_MEM_HOST && opts->device < 0)) &&
+            multi_direct(src_pos, src_mass, src_h, n, tgt_pos, m, kernel, want, out_pot, out_acc, opts))
+            return;
         Exec ex = make_exec(opts);
         StageTimer tm(ex.stream);
         if (m == 0) { finish_exec(ex); return; }
@@ -1057,12 +1088,7 @@ extern "C" int pnbx_direct(const double* src_pos, const double* src_mass, const 
             i_h.bind(src_h, (size_t)n, ex);
             if (!self) i_tgt.bind(tgt_pos, (size_t)3 * m, ex);
             tm.end();
-            if (ex.f64)
-                run_direct<double, TILE64>(ex, i_pos.d, i_mass.d, i_h.d, n, i_tgt.d, m, tgt_begin, kernel, want, o_pot.d,
-                                           o_acc.d, tm);
-            else
-                run_direct<float, TILE32>(ex, i_pos.d, i_mass.d, i_h.d, n, i_tgt.d, m, tgt_begin, kernel, want, o_pot.d,
-                                          o_acc.d, tm);
+            direct_on_device(ex, i_pos.d, i_mass.d, i_h.d, n, i_tgt.d, m, tgt_begin, kernel, want, o_pot.d, o_acc.d, tm);
         }
         tm.begin("direct.d2h");
         o_pot.finish(ex);

@@ -23,11 +23,15 @@ struct Lane {  // per staging thread: two pinned buffers, one stream, two events
     void* buf[2] = {nullptr, nullptr};
     cudaStream_t s = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
-    int device = -1;
+    bool ready = false;
 };
 
-std::mutex g_mu;
-Lane g_lanes[MAX_THREADS];
+// Lanes are per DEVICE (a multi-device call stages on all its devices at once); one staged transfer at a time per
+// device.
+constexpr int MAX_DEVICES = 64;
+std::mutex g_mu[MAX_DEVICES];
+Lane g_lanes[MAX_DEVICES][MAX_THREADS];
+thread_local int tl_threads_override = -1;
 
 int staging_threads() {
     static const int n = [] {
@@ -37,7 +41,7 @@ int staging_threads() {
         if (hw && (unsigned)v > hw) v = (int)hw;
         return std::max(0, std::min(v, MAX_THREADS));
     }();
-    return n;
+    return tl_threads_override >= 0 ? std::min(tl_threads_override, n) : n;
 }
 
 bool is_pageable(const void* p) {
@@ -49,18 +53,28 @@ bool is_pageable(const void* p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
-void prepare_lane(Lane& L, int device) {
-    if (L.device == device && L.s) return;
-    if (L.s) {  // lanes are per process; re-home them if the device changed
-        cudaStreamDestroy(L.s);
-        for (int i = 0; i < 2; ++i) { cudaEventDestroy(L.ev[i]); cudaFreeHost(L.buf[i]); }
-    }
-    PNBX_CUDA(cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
+void teardown_lane(Lane& L) {
+    if (L.s) cudaStreamDestroy(L.s);
     for (int i = 0; i < 2; ++i) {
-        PNBX_CUDA(cudaHostAlloc(&L.buf[i], CHUNK, cudaHostAllocDefault));
-        PNBX_CUDA(cudaEventCreateWithFlags(&L.ev[i], cudaEventDisableTiming));
+        if (L.ev[i]) cudaEventDestroy(L.ev[i]);
+        if (L.buf[i]) cudaFreeHost(L.buf[i]);
     }
-    L.device = device;
+    L = Lane{};
+}
+// The current device is the lane's device (staged_copy runs after make_exec selected it).
+void prepare_lane(Lane& L) {
+    if (L.ready) return;
+    try {
+        PNBX_CUDA(cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            PNBX_CUDA(cudaHostAlloc(&L.buf[i], CHUNK, cudaHostAllocPortable));
+            PNBX_CUDA(cudaEventCreateWithFlags(&L.ev[i], cudaEventDisableTiming));
+        }
+    } catch (...) {
+        teardown_lane(L);  // never leave a half-built lane behind
+        throw;
+    }
+    L.ready = true;
 }
 
 // dir = 0: host -> device, 1: device -> host. Runs the chunks k, k+nt, k+2nt, ... of lane k.
@@ -96,18 +110,25 @@ void lane_work(Lane& L, int device, int k, int nt, char* dev, char* host, size_t
         e = cudaEventSynchronize(L.ev[b]);
         if (dir == 1 && e == cudaSuccess) memcpy(host + pending_off[b], L.buf[b], pending_len[b]);
     }
+    if (e != cudaSuccess) cudaStreamSynchronize(L.s);  // nothing of this lane may still be in flight when we report
     *err = e;
 }
 
+struct EventHolder {
+    cudaEvent_t e = nullptr;
+    ~EventHolder() { if (e) cudaEventDestroy(e); }
+};
+
 void staged_copy(void* dev, void* host, size_t bytes, int dir, const Exec& ex) {
     const int nt = staging_threads();
-    std::lock_guard<std::mutex> lock(g_mu);  // one staged transfer at a time per process (the lanes are shared)
-    cudaEvent_t ready;
-    PNBX_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    PNBX_CUDA(cudaEventRecord(ready, ex.stream));  // allocation of `dev` / the kernels that produced it
+    const int d = ex.device < MAX_DEVICES ? ex.device : 0;
+    std::lock_guard<std::mutex> lock(g_mu[d]);
+    EventHolder ready;
+    PNBX_CUDA(cudaEventCreateWithFlags(&ready.e, cudaEventDisableTiming));
+    PNBX_CUDA(cudaEventRecord(ready.e, ex.stream));  // allocation of `dev` / the kernels that produced it
     for (int k = 0; k < nt; ++k) {
-        prepare_lane(g_lanes[k], ex.device);
-        PNBX_CUDA(cudaStreamWaitEvent(g_lanes[k].s, ready, 0));
+        prepare_lane(g_lanes[d][k]);
+        PNBX_CUDA(cudaStreamWaitEvent(g_lanes[d][k].s, ready.e, 0));
     }
     cudaError_t errs[MAX_THREADS];
     for (int k = 0; k < MAX_THREADS; ++k) errs[k] = cudaSuccess;
@@ -116,7 +137,7 @@ void staged_copy(void* dev, void* host, size_t bytes, int dir, const Exec& ex) {
     bool spawn_failed = false;
     for (int k = 0; k < nt; ++k) {
         try {
-            th[k] = std::thread(lane_work, std::ref(g_lanes[k]), ex.device, k, nt, (char*)dev, (char*)host, bytes, dir, &errs[k]);
+            th[k] = std::thread(lane_work, std::ref(g_lanes[d][k]), ex.device, k, nt, (char*)dev, (char*)host, bytes, dir, &errs[k]);
             ++started;
         } catch (const std::system_error&) {  // out of threads: the chunks of the missing lanes would be lost
             spawn_failed = true;
@@ -124,7 +145,6 @@ void staged_copy(void* dev, void* host, size_t bytes, int dir, const Exec& ex) {
         }
     }
     for (int k = 0; k < started; ++k) th[k].join();
-    cudaEventDestroy(ready);
     if (spawn_failed) throw ArgError{PNBX_ERR_CUDA, "staged host<->device copy: could not start the staging threads"};
     for (int k = 0; k < nt; ++k)
         if (errs[k] != cudaSuccess) throw CudaError{errs[k], "staged host<->device copy", __FILE__, __LINE__};
@@ -133,6 +153,8 @@ void staged_copy(void* dev, void* host, size_t bytes, int dir, const Exec& ex) {
 }
 
 }  // namespace
+
+void set_staging_threads_for_this_thread(int n) { tl_threads_override = n; }
 
 void copy_h2d(void* dev, const void* host, size_t bytes, const Exec& ex) {
     if (bytes >= STAGE_MIN && staging_threads() > 0 && is_pageable(host)) {

@@ -5,6 +5,9 @@
 // the reference's own descent arithmetic, radix sort, level-by-level node emission from sorted key
 // ranges, then a renumbering pass.
 #pragma once
+#include <functional>
+#include <memory>
+
 #include "common.cuh"
 
 namespace pnbx {
@@ -33,6 +36,22 @@ struct alignas(64) NodeRec {
 static_assert(sizeof(NodeRec) == 64, "NodeRec must be one 64-byte record");
 
 struct pnbx_tree_impl {
+    // All of the tree's memory is allocated, built and freed on `stream`, the library's per-device tree stream (never a
+    // caller's). Evaluations may run on any other stream: they wait for `ready` (recorded after every build / setter)
+    // and, when they finish, make the tree stream wait for them, so a later setter or the destructor can never free or
+    // overwrite what a walk is still reading.
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ready = nullptr;
+    Arena a_src, a_topo, a_payload;  // slabs behind the views below (n-sized, node-sized, payload)
+    pnbx_tree_impl() = default;
+    pnbx_tree_impl(const pnbx_tree_impl&) = delete;
+    pnbx_tree_impl& operator=(const pnbx_tree_impl&) = delete;
+    ~pnbx_tree_impl();
+
+    // PNBX_DEVICES: this tree is the copy on multi_devs[0]; replicas[r-1] is the identical tree on multi_devs[r]
+    std::vector<std::unique_ptr<pnbx_tree_impl>> replicas;
+    std::vector<int> multi_devs;
+
     int device = 0;
     int64_t n = 0;
     int64_t leaf_capacity = 1;
@@ -78,8 +97,28 @@ struct pnbx_tree_impl {
     DevBuf<NodeRec> rec;               // walk records (reference numbering)
 };
 
+// tree_build.cu — construction in phases, shared by the single- and multi-device entry points.
+// tree_init: device, stream, options and the n-sized slab (the caller then fills t.pos / t.mass / t.h on t.stream);
+// tree_build: keys, sort, topology and, iff has_mass, the payloads (Octree::new, gravity.rs:121-226).
+void tree_init(pnbx_tree_impl& t, int device, int64_t n, int64_t leaf_capacity, int multipole_order, int kernel,
+               bool has_mass, bool has_h);
+void tree_build(pnbx_tree_impl& t, StageTimer& tm);
+void tree_build_mass(pnbx_tree_impl& t, StageTimer& tm);              // build_mass (tree.rs:968-1012) on t.stream
+void tree_mark_ready(pnbx_tree_impl& t);                              // record `ready` on t.stream
+void tree_begin_use(const pnbx_tree_impl& t, cudaStream_t s);         // s waits for the tree to be ready
+void tree_end_use(const pnbx_tree_impl& t, cudaStream_t s);           // t.stream waits for the work queued on s
+void stream_wait_stream(cudaStream_t waiter, cudaStream_t on, int device);
+
 // tree_walk.cu
 void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int64_t m, int64_t tgt_begin,
-               double theta, int want, double* d_pot, double* d_acc, StageTimer& tm, unsigned long long* d_counters);
+               double theta, int want, double* d_pot, double* d_acc, StageTimer& tm, unsigned long long* d_counters,
+               const OutSlices* slices = nullptr);
+
+// multi.cu
+bool multi_tree_create(pnbx_tree_impl& primary, const double* pos, const double* mass, const double* h, int64_t n,
+                       int64_t leaf_capacity, int multipole_order, int kernel, const pnbx_opts* opts);
+void multi_tree_for_each(pnbx_tree_impl& primary, const std::function<void(pnbx_tree_impl&)>& fn);
+bool multi_tree_eval(pnbx_tree_impl& primary, const double* tgt_pos, int64_t m, double theta, int want, double* out_pot,
+                     double* out_acc, const pnbx_opts* opts);
 
 }  // namespace pnbx

@@ -7,8 +7,13 @@
 //                      reference's creation-order numbering, first_subnode / next_branch links
 //   K6 payloads        tree.rs:866-965, 1014-1067: mass/COM, hmax, P2M/M2M, bottom-up per level,
 //                      float64 with the reference's operation order (no FMA contraction)
+#include <cstring>
+#include <mutex>
+
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/reverse_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "multipole.cuh"
 #include "tree.cuh"
@@ -661,31 +666,41 @@ void inclusive_sum_u32(const uint32_t* in, uint32_t* out, int64_t n, cudaStream_
 }
 
 // Builds the topology from sorted keys. Returns false if `max_level` was reached with an over-full cell.
-bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const double* root4, const uint64_t* skhi, const uint64_t* sklo,
-                    int max_level, StageTimer& tm) {
+// `scratch` holds the n-sized temporaries (laid out by the caller together with the keys), `s2` the node-sized ones.
+struct KeyScratch {
+    uint64_t* skhi; uint64_t* sklo;  // sorted keys
+    int8_t* bq; int8_t* Dq; int32_t* nodes_here; int32_t* base;
+};
+bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const KeyScratch& k, int max_level, StageTimer& tm) {
     const int64_t n = t.n;
     const int64_t cap = t.leaf_capacity;
-    auto alloc_final = [&](int64_t nn) {
+    const double* root4 = t.root4.p;
+    const uint64_t* skhi = k.skhi;
+    const uint64_t* sklo = k.sklo;
+    FinalArrays f{};
+    auto layout_final = [&](int64_t nn) {
         t.nn = nn;
-        t.center.alloc((size_t)3 * nn, s); t.half.alloc((size_t)nn, s); t.node_depth.alloc((size_t)nn, s);
-        t.node_start.alloc((size_t)nn, s); t.node_count.alloc((size_t)nn, s);
-        t.first_subnode.alloc((size_t)nn, s); t.next_branch.alloc((size_t)nn, s);
-        t.path_hi.alloc((size_t)nn, s); t.path_lo.alloc((size_t)nn, s);
-        t.node_nchild.alloc((size_t)nn, s);
-        return FinalArrays{t.center.p, t.half.p, t.node_depth.p, t.node_start.p, t.node_count.p, t.first_subnode.p,
-                           t.next_branch.p, t.path_hi.p, t.path_lo.p, t.node_nchild.p};
+        for (int pass = 0; pass < 2; ++pass) {
+            Arena& A = t.a_topo;
+            A.take(t.center, (size_t)3 * nn); A.take(t.half, (size_t)nn); A.take(t.node_depth, (size_t)nn);
+            A.take(t.node_start, (size_t)nn); A.take(t.node_count, (size_t)nn);
+            A.take(t.first_subnode, (size_t)nn); A.take(t.next_branch, (size_t)nn);
+            A.take(t.path_hi, (size_t)nn); A.take(t.path_lo, (size_t)nn);
+            A.take(t.node_nchild, (size_t)nn); A.take(t.level_ids, (size_t)nn);
+            if (pass == 0) A.commit(s);
+        }
+        f = FinalArrays{t.center.p, t.half.p, t.node_depth.p, t.node_start.p, t.node_count.p, t.first_subnode.p,
+                        t.next_branch.p, t.path_hi.p, t.path_lo.p, t.node_nchild.p};
     };
     if (n == 0) {  // the reference's empty tree: one root leaf (tree.rs:658-734 with no points)
-        FinalArrays f = alloc_final(1);
+        layout_final(1);
         PNBX_LAUNCH(empty_root, 1, 1, 0, s, root4, f);
         t.n_leaves = 1; t.depth = 0; t.n_internal = 0;
         t.ilevel_off.assign(2, 0);
-        t.level_ids.alloc(1, s);
         return true;
     }
     tm.begin("octree.leaf_levels");
-    DevBuf<int8_t> bq((size_t)n, s), Dq((size_t)n, s), Pm, Sm;
-    DevBuf<int32_t> nodes_here((size_t)n, s), base((size_t)n + 1, s);
+    DevBuf<int8_t> Pm, Sm;
     DevBuf<unsigned long long> hist(2 * MAX_LEVELS + 2, s);
     PNBX_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), s));
     const int64_t nw = n - cap;
@@ -695,9 +710,8 @@ bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const double* root4, cons
         DevBuf<int8_t> W((size_t)nw, s);
         Pm.alloc((size_t)nw, s); Sm.alloc((size_t)nw, s);
         PNBX_LAUNCH(window_digits, nblk(nw), 256, 0, s, skhi, sklo, nw, cap, W.p);
-        cub::CountingInputIterator<int64_t> cnt(0);
-        cub::TransformInputIterator<int64_t, BlockOf, cub::CountingInputIterator<int64_t>> kf(cnt, BlockOf{cap + 1});
-        cub::TransformInputIterator<int64_t, RevBlockOf, cub::CountingInputIterator<int64_t>> kr(cnt, RevBlockOf{cap + 1, nw - 1});
+        auto kf = thrust::make_transform_iterator(thrust::make_counting_iterator<int64_t>(0), BlockOf{cap + 1});
+        auto kr = thrust::make_transform_iterator(thrust::make_counting_iterator<int64_t>(0), RevBlockOf{cap + 1, nw - 1});
         size_t bytes = 0;
         PNBX_CUDA(cub::DeviceScan::InclusiveScanByKey(nullptr, bytes, kf, W.p, Pm.p, MaxI8{}, (int)nw, cub::Equality{}, s));
         DevBuf<uint8_t> tmp(bytes, s);
@@ -710,9 +724,9 @@ bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const double* root4, cons
         PNBX_CUDA(cub::DeviceScan::InclusiveScanByKey(tmp2.get(), bytes2, kr, rin, rout, MaxI8{}, (int)nw, cub::Equality{}, s));
         launch_counter() += 2;
     }
-    PNBX_LAUNCH(leaf_levels, nblk(n), 256, 0, s, skhi, sklo, n, cap, max_level, Pm.p, Sm.p, bq.p, Dq.p, nodes_here.p, hist.p);
-    PNBX_CUDA(cudaMemsetAsync(base.p + n, 0, 4, s));
-    exclusive_sum(nodes_here.p, base.p, n, s);
+    PNBX_LAUNCH(leaf_levels, nblk(n), 256, 0, s, skhi, sklo, n, cap, max_level, Pm.p, Sm.p, k.bq, k.Dq, k.nodes_here, hist.p);
+    PNBX_CUDA(cudaMemsetAsync(k.base + n, 0, 4, s));
+    exclusive_sum(k.nodes_here, k.base, n, s);
     // the one synchronisation of the build: per-level node counts (allocation sizes) and the overflow flag
     unsigned long long hh[2 * MAX_LEVELS + 2];
     PNBX_CUDA(cudaMemcpyAsync(hh, hist.p, sizeof(hh), cudaMemcpyDeviceToHost, s));
@@ -730,34 +744,37 @@ bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const double* root4, cons
     if (nn >= ((int64_t)1 << 31) - 16) throw ArgError{PNBX_ERR_ARG, "octree has more than 2^31 nodes"};
 
     tm.begin("octree.emit_nodes");
-    DevBuf<uint32_t> d_start((size_t)nn, s), d_count((size_t)nn, s), d_parent((size_t)nn, s), d_mask((size_t)nn, s);
-    DevBuf<uint8_t> d_level((size_t)nn, s), d_digit((size_t)nn, s);
-    DevBuf<double> d_center((size_t)3 * nn, s), d_half((size_t)nn, s);
-    DevBuf<uint64_t> d_phi((size_t)nn, s), d_plo((size_t)nn, s);
-    PNBX_CUDA(cudaMemsetAsync(d_mask.p, 0, d_mask.bytes(), s));
-    DfsNodes d{d_start.p, d_count.p, d_parent.p, d_mask.p, d_level.p, d_digit.p, d_center.p, d_half.p, d_phi.p, d_plo.p};
-    PNBX_LAUNCH(emit_nodes, nblk(n, 128), 128, 0, s, skhi, sklo, n, bq.p, Dq.p, nodes_here.p, base.p, root4, d);
+    layout_final(nn);
+    Arena S2;  // node-sized temporaries: the depth-first node list and the renumbering arrays
+    DfsNodes d{};
+    int32_t *nchild = nullptr, *scan = nullptr, *ref = nullptr, *sortval = nullptr;
+    uint8_t *sortkey = nullptr, *key_out = nullptr, *sort_tmp = nullptr;
+    size_t sort_bytes = 0;
+    PNBX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, sortkey, key_out, sortval, t.level_ids.p, (int)nn, 0, 7, s));
+    for (int pass = 0; pass < 2; ++pass) {
+        d.start = S2.take<uint32_t>((size_t)nn); d.count = S2.take<uint32_t>((size_t)nn);
+        d.parent = S2.take<uint32_t>((size_t)nn); d.mask = S2.take<uint32_t>((size_t)nn);
+        d.level = S2.take<uint8_t>((size_t)nn); d.digit = S2.take<uint8_t>((size_t)nn);
+        d.center = S2.take<double>((size_t)3 * nn); d.half = S2.take<double>((size_t)nn);
+        d.phi = S2.take<uint64_t>((size_t)nn); d.plo = S2.take<uint64_t>((size_t)nn);
+        nchild = S2.take<int32_t>((size_t)nn); scan = S2.take<int32_t>((size_t)nn); ref = S2.take<int32_t>((size_t)nn);
+        sortval = S2.take<int32_t>((size_t)nn); sortkey = S2.take<uint8_t>((size_t)nn); key_out = S2.take<uint8_t>((size_t)nn);
+        sort_tmp = S2.take<uint8_t>(sort_bytes);
+        if (pass == 0) S2.commit(s);
+    }
+    PNBX_CUDA(cudaMemsetAsync(d.mask, 0, (size_t)nn * 4, s));
+    PNBX_LAUNCH(emit_nodes, nblk(n, 128), 128, 0, s, skhi, sklo, n, k.bq, k.Dq, k.nodes_here, k.base, root4, d);
     tm.end();
 
     // ---- reference numbering, links, scatter
     tm.begin("octree.renumber_links");
-    DevBuf<int32_t> nchild((size_t)nn, s), scan((size_t)nn, s), ref((size_t)nn, s), sortval((size_t)nn, s);
-    DevBuf<uint8_t> sortkey((size_t)nn, s);
-    PNBX_LAUNCH(child_counts, nblk(nn), 256, 0, s, d_mask.p, nn, nchild.p);
-    exclusive_sum(nchild.p, scan.p, nn, s);
-    PNBX_LAUNCH(assign_ref_ids, nblk(nn), 256, 0, s, d_parent.p, d_digit.p, d_mask.p, scan.p, nn, ref.p);
-    FinalArrays f = alloc_final(nn);
-    PNBX_LAUNCH(scatter_nodes, nblk(nn), 256, 0, s, d, scan.p, ref.p, base.p, nn, n, f, sortkey.p, sortval.p);
+    PNBX_LAUNCH(child_counts, nblk(nn), 256, 0, s, d.mask, nn, nchild);
+    exclusive_sum(nchild, scan, nn, s);
+    PNBX_LAUNCH(assign_ref_ids, nblk(nn), 256, 0, s, d.parent, d.digit, d.mask, scan, nn, ref);
+    PNBX_LAUNCH(scatter_nodes, nblk(nn), 256, 0, s, d, scan, ref, k.base, nn, n, f, sortkey, sortval);
     // internal nodes grouped by level (bottom-up payload sweeps): stable 7-bit sort of the DFS list
-    t.level_ids.alloc((size_t)nn, s);
-    {
-        DevBuf<uint8_t> key_out((size_t)nn, s);
-        size_t bytes = 0;
-        PNBX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, sortkey.p, key_out.p, sortval.p, t.level_ids.p, (int)nn, 0, 7, s));
-        DevBuf<uint8_t> tmp(bytes, s);
-        PNBX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), bytes, sortkey.p, key_out.p, sortval.p, t.level_ids.p, (int)nn, 0, 7, s));
-        ++launch_counter();
-    }
+    PNBX_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, sortkey, key_out, sortval, t.level_ids.p, (int)nn, 0, 7, s));
+    ++launch_counter();
     t.depth = depth;
     t.n_internal = ni;
     t.n_leaves = nn - ni;
@@ -766,11 +783,11 @@ bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const double* root4, cons
     // ---- ascending original index inside every leaf
     tm.begin("octree.leaf_order");
     if (cap <= LEAF_SORT_MAX) {
-        PNBX_LAUNCH(sort_leaves_small, nblk(n, 128), 128, 0, s, nodes_here.p, n, t.perm.p);
+        PNBX_LAUNCH(sort_leaves_small, nblk(n, 128), 128, 0, s, k.nodes_here, n, t.perm.p);
     } else {
         DevBuf<uint32_t> lflag((size_t)n, s), lord_sorted((size_t)n, s), lord_orig((size_t)n, s), lord_out((size_t)n, s);
         DevBuf<uint32_t> iota((size_t)n, s), perm2((size_t)n, s);
-        PNBX_LAUNCH(head_flags, nblk(n), 256, 0, s, nodes_here.p, n, lflag.p);
+        PNBX_LAUNCH(head_flags, nblk(n), 256, 0, s, k.nodes_here, n, lflag.p);
         inclusive_sum_u32(lflag.p, lord_sorted.p, n, s);
         PNBX_LAUNCH(leaf_ordinal_to_particles, nblk(n), 256, 0, s, lord_sorted.p, t.perm.p, n, lord_orig.p);
         PNBX_LAUNCH(iota_u32, nblk(n), 256, 0, s, iota.p, n);
@@ -785,29 +802,108 @@ bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const double* root4, cons
 void gather_sorted_sources(pnbx_tree_impl& t, cudaStream_t s) {
     const int64_t n = t.n;
     if (n == 0) return;
-    if (!t.spos.p) t.spos.alloc((size_t)3 * n, s);
-    if (t.has_mass && !t.smass.p) t.smass.alloc((size_t)n, s);
     PNBX_LAUNCH(gather_sources, nblk(n), 256, 0, s, t.pos.p, t.has_mass ? t.mass.p : nullptr, t.perm.p, n, t.spos.p,
                 t.has_mass ? t.smass.p : nullptr);
 }
 void gather_sorted_soft(pnbx_tree_impl& t, cudaStream_t s) {
     const int64_t n = t.n;
     if (!t.has_h || n == 0) return;
-    if (!t.sh.p) { t.sh.alloc((size_t)n, s); t.sh32.alloc((size_t)n + 4, s); }
+    if (!t.sh.p) { t.sh.alloc((size_t)n, s); t.sh32.alloc((size_t)n + 4, s); }  // softenings given after the build
     PNBX_LAUNCH(gather_soft, nblk(n), 256, 0, s, t.h.p, t.perm.p, n, t.sh.p, t.sh32.p);
 }
 
+thread_local cudaEvent_t tl_order_event[KernelEvents::MAXDEV] = {};
+cudaEvent_t order_event(int device) {
+    cudaEvent_t& e = tl_order_event[device < KernelEvents::MAXDEV ? device : 0];
+    if (!e) PNBX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return e;
+}
+
+}  // namespace
+
+// `waiter` waits for everything queued on `on` so far. The per-thread event may be re-recorded right away: a wait
+// captures the record that preceded it.
+void stream_wait_stream(cudaStream_t waiter, cudaStream_t on, int device) {
+    if (waiter == on) return;
+    cudaEvent_t e = order_event(device);
+    PNBX_CUDA(cudaEventRecord(e, on));
+    PNBX_CUDA(cudaStreamWaitEvent(waiter, e, 0));
+}
+void tree_mark_ready(pnbx_tree_impl& t) { PNBX_CUDA(cudaEventRecord(t.ready, t.stream)); }
+void tree_begin_use(const pnbx_tree_impl& t, cudaStream_t s) {
+    if (s != t.stream) PNBX_CUDA(cudaStreamWaitEvent(s, t.ready, 0));
+}
+void tree_end_use(const pnbx_tree_impl& t, cudaStream_t s) { stream_wait_stream(t.stream, s, t.device); }
+
+pnbx_tree_impl::~pnbx_tree_impl() {
+    replicas.clear();  // each on its own device
+    cudaSetDevice(device);
+    // everything is freed on the tree's own stream, which is ordered after every evaluation (tree_end_use)
+    DevBuf<double>* d64[] = {&pos, &mass, &h, &spos, &smass, &sh, &center, &half, &nmass, &ncom, &hmax, &moments, &root4};
+    for (auto* b : d64) b->release();
+    key_hi.release(); key_lo.release(); perm.release(); src32.release(); sh32.release();
+    node_depth.release(); node_nchild.release(); node_start.release(); node_count.release();
+    first_subnode.release(); next_branch.release(); path_hi.release(); path_lo.release(); level_ids.release();
+    moments32.release(); rec.release();
+    a_payload.release(); a_topo.release(); a_src.release();
+    if (ready) cudaEventDestroy(ready);
+}
+
+// One library-owned stream per device carries the memory traffic (allocate, build, free) of EVERY tree on that
+// device. Blocks freed by one tree are then reusable by the next build at once (same-stream reuse in the pool; with
+// a stream per tree the pool fell back to fresh driver allocations, 10-70 ms per GB-sized slab).
+cudaStream_t device_tree_stream(int device) {
+    static std::mutex mu;
+    static cudaStream_t streams[KernelEvents::MAXDEV] = {};
+    if (device < 0 || device >= KernelEvents::MAXDEV) throw ArgError{PNBX_ERR_ARG, "device ordinal out of range"};
+    std::lock_guard<std::mutex> lock(mu);
+    if (!streams[device]) PNBX_CUDA(cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking));
+    return streams[device];
+}
+
+void tree_init(pnbx_tree_impl& t, int device, int64_t n, int64_t leaf_capacity, int multipole_order, int kernel,
+               bool has_mass, bool has_h) {
+    t.device = device;
+    t.n = n;
+    t.leaf_capacity = std::max<int64_t>(leaf_capacity, 1);  // tree.rs:701
+    t.order_raw = multipole_order;
+    t.order = std::min(multipole_order, 5);                 // tree.rs:1020
+    t.kernel = kernel;
+    t.has_mass = has_mass;
+    t.has_h = has_h;
+    t.stream = device_tree_stream(device);
+    PNBX_CUDA(cudaEventCreateWithFlags(&t.ready, cudaEventDisableTiming));
+    const size_t m = (size_t)std::max<int64_t>(n, 1);
+    for (int pass = 0; pass < 2; ++pass) {
+        Arena& A = t.a_src;
+        A.take(t.root4, 4);
+        A.take(t.pos, 3 * m); A.take(t.mass, m);
+        if (has_h) { A.take(t.h, m); A.take(t.sh, m); A.take(t.sh32, m + 4); }
+        A.take(t.key_hi, m); A.take(t.perm, m);
+        A.take(t.spos, 3 * m); A.take(t.smass, m); A.take(t.src32, m);
+        if (pass == 0) A.commit(t.stream);
+    }
+}
+
 // tree.rs:968-1012
-void build_mass_payload(pnbx_tree_impl& t, cudaStream_t s, StageTimer& tm) {
+void tree_build_mass(pnbx_tree_impl& t, StageTimer& tm) {
+    cudaStream_t s = t.stream;
     const int64_t nn = t.nn;
-    tm.begin("octree.build_mass_payload");
+    tm.begin("octree.payload.alloc_gather");
     gather_sorted_sources(t, s);  // masses may have been replaced
-    t.nmass.alloc((size_t)nn, s);
-    t.ncom.alloc((size_t)3 * nn, s);
     t.has_hmax = t.has_h;
-    if (t.has_hmax) t.hmax.alloc((size_t)nn, s); else t.hmax.release();
     t.n_moments = mp::stored_coeffs(t.order);
-    t.moments.alloc((size_t)nn * t.n_moments, s);
+    t.rec32 = mp::fast_rec_floats(t.order);
+    for (int pass = 0; pass < 2; ++pass) {
+        Arena& A = t.a_payload;
+        if (pass == 0) A.release();  // rebuild: the old slab goes back to the pool in stream order
+        A.take(t.nmass, (size_t)nn); A.take(t.ncom, (size_t)3 * nn);
+        if (t.has_hmax) A.take(t.hmax, (size_t)nn); else t.hmax.release();
+        A.take(t.moments, (size_t)nn * t.n_moments);
+        A.take(t.rec, (size_t)nn);
+        A.take(t.moments32, (size_t)nn * t.rec32);
+        if (pass == 0) A.commit(s);
+    }
     PayloadArgs a;
     a.start = t.node_start.p; a.pcount = t.node_count.p; a.nchild = t.node_nchild.p; a.first_subnode = t.first_subnode.p;
     a.spos = t.spos.p; a.smass = t.has_mass ? t.smass.p : nullptr; a.sh = t.has_h ? t.sh.p : nullptr;
@@ -824,39 +920,141 @@ void build_mass_payload(pnbx_tree_impl& t, cudaStream_t s, StageTimer& tm) {
         PNBX_P(0) PNBX_P(2) PNBX_P(3) PNBX_P(4) PNBX_P(5)
 #undef PNBX_P
     };
+    tm.end();
+    tm.begin("octree.payload.leaves");
     a.ids = nullptr;
     a.count = nn;
     launch(true);  // every leaf of every level at once
+    tm.end();
+    tm.begin("octree.payload.internal");
     for (int d = (int)t.ilevel_off.size() - 2; d >= 0; --d) {  // internal nodes only, deepest level first
         a.ids = t.level_ids.p + t.ilevel_off[d];
         a.count = t.ilevel_off[d + 1] - t.ilevel_off[d];
         if (a.count > 0) launch(false);
     }
-    t.rec.alloc((size_t)nn, s);
+    tm.end();
+    tm.begin("octree.payload.walk_records");
     PNBX_LAUNCH(build_walk_records, nblk(nn), 256, 0, s, t.nmass.p, t.ncom.p, t.half.p, t.has_hmax ? t.hmax.p : nullptr,
                 t.kernel == PNBX_KERNEL_SPLINE ? 1.0 : 2.8, t.node_nchild.p, t.node_start.p, t.node_count.p,
                 t.first_subnode.p, t.next_branch.p, nn, t.rec.p);
-    if (t.n > 0 && !t.src32.p) t.src32.alloc((size_t)t.n, s);
     PNBX_LAUNCH(merge_leaf_runs, nblk(nn), 256, 0, s, t.node_nchild.p, t.first_subnode.p, t.node_start.p, t.node_count.p,
                 t.next_branch.p, t.nmass.p, t.ncom.p, t.spos.p, t.has_mass ? t.smass.p : nullptr, nn, t.rec.p,
                 t.n > 0 ? t.src32.p : nullptr);
-    t.rec32 = mp::fast_rec_floats(t.order);
-    t.moments32.alloc((size_t)nn * t.rec32, s);
     PNBX_LAUNCH(pack_walk_moments, nblk(nn), 256, 0, s, t.moments.p, nn, t.order, t.n_moments, t.rec32, t.moments32.p);
     PNBX_CUDA(cudaGetLastError());
     t.has_payload = true;
     tm.end();
 }
 
-Exec tree_exec(const pnbx_tree_impl& t) {
-    pnbx_opts o{t.device, PNBX_MEM_HOST, 0, 0, nullptr};
-    return make_exec(&o);
+void tree_build(pnbx_tree_impl& t, StageTimer& tm) {
+    cudaStream_t s = t.stream;
+    const int64_t n = t.n;
+    if (n > 0) {
+        tm.begin("octree.bbox");
+        DevBuf<double> bb(6, s);
+        launch_bbox(t.pos.p, n, bb.p, s);
+        PNBX_LAUNCH(root_from_bbox, 1, 1, 0, s, bb.p, t.root4.p);
+        tm.end();
+    } else {
+        // empty point set: the reference gets a NaN-centred, half = 1e-6 root leaf of mass 0
+        static const double r4[4] = {0.0, 0.0, 0.0, 1e-6};
+        PNBX_CUDA(cudaMemcpyAsync(t.root4.p, r4, sizeof(r4), cudaMemcpyHostToDevice, s));
+    }
+    // keys + sort; first with the 21-level word only, the second word only if a level-21 cell is over-full
+    bool ok = false;
+    for (int attempt = 0; attempt < 2 && !ok; ++attempt) {
+        const bool two = attempt == 1;
+        const int levels = two ? KEY_LEVELS : KEY_LEVELS_HI;
+        const size_t m = (size_t)std::max<int64_t>(n, 1);
+        Arena S1;  // n-sized temporaries
+        KeyScratch k{};
+        uint32_t *iota = nullptr, *idx1 = nullptr;
+        uint64_t *tmpk = nullptr, *hi1 = nullptr;
+        uint8_t* sort_tmp = nullptr;
+        size_t sort_bytes = 0;
+        if (n > 0)
+            PNBX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k.skhi, k.skhi, iota, iota, (int)n, 0, 63, s));
+        if (two) t.key_lo.alloc(m, s);
+        for (int pass = 0; pass < 2; ++pass) {
+            k.skhi = S1.take<uint64_t>(m);
+            iota = S1.take<uint32_t>(m);
+            sort_tmp = S1.take<uint8_t>(sort_bytes);
+            k.bq = S1.take<int8_t>(m); k.Dq = S1.take<int8_t>(m);
+            k.nodes_here = S1.take<int32_t>(m); k.base = S1.take<int32_t>(m + 1);
+            if (two) {
+                k.sklo = S1.take<uint64_t>(m); tmpk = S1.take<uint64_t>(m); hi1 = S1.take<uint64_t>(m);
+                idx1 = S1.take<uint32_t>(m);
+            }
+            if (pass == 0) S1.commit(s);
+        }
+        if (n > 0) {
+            tm.begin("octree.keys_sort");
+            PNBX_LAUNCH(path_keys, nblk(n), 256, 0, s, t.pos.p, n, t.root4.p, levels, t.key_hi.p, two ? t.key_lo.p : nullptr);
+            PNBX_LAUNCH(iota_u32, nblk(n), 256, 0, s, iota, n);
+            auto sort63 = [&](const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout) {
+                size_t bytes = sort_bytes;
+                PNBX_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, kin, kout, vin, vout, (int)n, 0, 63, s));
+                ++launch_counter();
+            };
+            if (!two) {
+                sort63(t.key_hi.p, k.skhi, iota, t.perm.p);
+            } else {  // LSD over the two words: low word first, then a stable sort by the high word
+                sort63(t.key_lo.p, tmpk, iota, idx1);
+                PNBX_LAUNCH(gather_u32<uint64_t>, nblk(n), 256, 0, s, t.key_hi.p, idx1, n, hi1);
+                sort63(hi1, k.skhi, idx1, t.perm.p);
+                PNBX_LAUNCH(gather_u32<uint64_t>, nblk(n), 256, 0, s, t.key_lo.p, t.perm.p, n, k.sklo);
+            }
+            tm.end();
+        }
+        ok = build_topology(t, s, k, levels, tm);
+    }
+    if (!ok)
+        throw ArgError{PNBX_ERR_DEPTH,
+                       "octree deeper than 42 levels (more than leaf_capacity coincident or nearly coincident "
+                       "points); the reference would recurse without bound here"};
+    gather_sorted_soft(t, s);
+    if (t.has_mass) tree_build_mass(t, tm);  // gravity.rs:210-220
+    else gather_sorted_sources(t, s);
 }
 
-}  // namespace
 }  // namespace pnbx
 
 using namespace pnbx;
+
+namespace {
+Exec make_exec_for(int device, cudaStream_t s) {  // host-pointer context on an explicit device / stream (current device is set)
+    Exec ex;
+    ex.device = device;
+    ex.stream = s;
+    return ex;
+}
+pnbx_opts tree_opts(const pnbx_tree_impl& t, const pnbx_opts* opts) {
+    pnbx_opts o = opts ? *opts : pnbx_opts{-1, PNBX_MEM_HOST, 0, 0, nullptr, 0, 1, 0};
+    if (o.device < 0) o.device = t.device;
+    if (o.device != t.device) throw ArgError{PNBX_ERR_ARG, "tree lives on a different device"};
+    return o;
+}
+// copy an input array into a tree buffer on the tree's stream (host pointer: H2D, staged if pageable; device
+// pointer: ordered after the caller's stream)
+void copy_into_tree(pnbx_tree_impl& t, const Exec& ex, double* dst, const double* src, size_t count) {
+    if (!count) return;
+    if (ex.device_ptrs) {
+        PNBX_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToDevice, t.stream));
+    } else {
+        Exec tex = ex;
+        tex.stream = t.stream;
+        copy_h2d(dst, src, count * sizeof(double), tex);
+    }
+}
+// after a build / setter: publish, then either block (host arrays: the call is synchronous) or order the caller's
+// stream behind the tree's (device arrays: the caller may reuse its inputs in stream order)
+void tree_publish(pnbx_tree_impl& t, Exec& ex) {
+    tree_mark_ready(t);
+    if (ex.device_ptrs) PNBX_CUDA(cudaStreamWaitEvent(ex.stream, t.ready, 0));
+    else PNBX_CUDA(cudaStreamSynchronize(t.stream));
+    if (ex.own_stream) { cudaStreamDestroy(ex.stream); ex.own_stream = false; }
+}
+}  // namespace
 
 extern "C" int pnbx_tree_create(pnbx_tree** out, const double* pos, const double* mass, const double* h, int64_t n,
                                 int64_t leaf_capacity, int multipole_order, int kernel, const pnbx_opts* opts) {
@@ -869,145 +1067,127 @@ extern "C" int pnbx_tree_create(pnbx_tree** out, const double* pos, const double
         if (kernel != PNBX_KERNEL_PLUMMER && kernel != PNBX_KERNEL_SPLINE)
             throw ArgError{PNBX_ERR_ARG, "kernel must be 0 (Plummer) or 1 (CubicSplineW2)"};
         if (leaf_capacity < 0 || multipole_order < 0) throw ArgError{PNBX_ERR_ARG, "negative leaf_capacity / multipole_order"};
-        Exec ex = make_exec(opts);
-        cudaStream_t s = ex.stream;
-        StageTimer tm(s);
         auto t = std::make_unique<pnbx_tree_impl>();
-        t->device = ex.device;
-        t->n = n;
-        t->leaf_capacity = std::max<int64_t>(leaf_capacity, 1);  // tree.rs:701
-        t->order_raw = multipole_order;
-        t->order = std::min(multipole_order, 5);                 // tree.rs:1020
-        t->kernel = kernel;
-        t->has_mass = mass != nullptr;
-        t->has_h = h != nullptr;
-
+        // PNBX_DEVICES: host arrays, no explicit device -> identical trees on all listed GPUs (multi.cu)
+        if ((!opts || (opts->mem_space == PNBX_MEM_HOST && opts->device < 0)) &&
+            multi_tree_create(*t, pos, mass, h, n, leaf_capacity, multipole_order, kernel, opts)) {
+            *out = reinterpret_cast<pnbx_tree*>(t.release());
+            return;
+        }
+        Exec ex = make_exec(opts);
+        tree_init(*t, ex.device, n, leaf_capacity, multipole_order, kernel, mass != nullptr, h != nullptr);
+        StageTimer tm(t->stream);
+        if (ex.device_ptrs) stream_wait_stream(t->stream, ex.stream, ex.device);  // inputs produced on the caller's stream
         tm.begin("octree.copy_in");
-        auto copy_in = [&](DevBuf<double>& dst, const double* src, size_t cnt) {
-            dst.alloc(std::max<size_t>(cnt, 1), s);
-            if (!cnt) return;
-            if (ex.device_ptrs) PNBX_CUDA(cudaMemcpyAsync(dst.p, src, cnt * sizeof(double), cudaMemcpyDeviceToDevice, s));
-            else copy_h2d(dst.p, src, cnt * sizeof(double), ex);
-        };
-        copy_in(t->pos, pos, (size_t)3 * n);
-        if (mass) copy_in(t->mass, mass, (size_t)n);
-        if (h) copy_in(t->h, h, (size_t)n);
+        copy_into_tree(*t, ex, t->pos.p, pos, (size_t)3 * n);
+        if (mass) copy_into_tree(*t, ex, t->mass.p, mass, (size_t)n);
+        if (h) copy_into_tree(*t, ex, t->h.p, h, (size_t)n);
         tm.end();
-
-        DevBuf<double> bb(6, s);
-        t->root4.alloc(4, s);  // root cube {cx, cy, cz, half} (tree.rs:628-654); stays on the device: no host round trip
-        if (n > 0) {
-            tm.begin("octree.bbox");
-            launch_bbox(t->pos.p, n, bb.p, s);
-            PNBX_LAUNCH(root_from_bbox, 1, 1, 0, s, bb.p, t->root4.p);
-            tm.end();
-        } else {
-            // empty point set: the reference gets a NaN-centred, half = 1e-6 root leaf of mass 0
-            static const double r4[4] = {0.0, 0.0, 0.0, 1e-6};
-            PNBX_CUDA(cudaMemcpyAsync(t->root4.p, r4, sizeof(r4), cudaMemcpyHostToDevice, s));
-        }
-
-        // keys + sort; first with the 21-level word only, the second word only if a level-21 cell is over-full
-        t->key_hi.alloc((size_t)std::max<int64_t>(n, 1), s);
-        t->key_lo.alloc((size_t)std::max<int64_t>(n, 1), s);
-        t->perm.alloc((size_t)std::max<int64_t>(n, 1), s);
-        bool ok = false;
-        for (int attempt = 0; attempt < 2 && !ok; ++attempt) {
-            const bool use_lo = attempt == 1;
-            const int levels = use_lo ? KEY_LEVELS : KEY_LEVELS_HI;
-            DevBuf<uint64_t> skhi((size_t)std::max<int64_t>(n, 1), s), sklo;
-            if (n > 0) {
-                tm.begin("octree.keys_sort");
-                PNBX_LAUNCH(path_keys, nblk(n), 256, 0, s, t->pos.p, n, t->root4.p, levels, t->key_hi.p, t->key_lo.p);
-                DevBuf<uint32_t> iota((size_t)n, s);
-                PNBX_LAUNCH(iota_u32, nblk(n), 256, 0, s, iota.p, n);
-                if (!use_lo) {
-                    sort_pairs<uint64_t>(t->key_hi.p, skhi.p, iota.p, t->perm.p, n, 63, s);
-                } else {
-                    DevBuf<uint64_t> tmpk((size_t)n, s), hi1((size_t)n, s);
-                    DevBuf<uint32_t> idx1((size_t)n, s);
-                    sort_pairs<uint64_t>(t->key_lo.p, tmpk.p, iota.p, idx1.p, n, 63, s);
-                    PNBX_LAUNCH(gather_u32<uint64_t>, nblk(n), 256, 0, s, t->key_hi.p, idx1.p, n, hi1.p);
-                    sort_pairs<uint64_t>(hi1.p, skhi.p, idx1.p, t->perm.p, n, 63, s);
-                    sklo.alloc((size_t)n, s);
-                    PNBX_LAUNCH(gather_u32<uint64_t>, nblk(n), 256, 0, s, t->key_lo.p, t->perm.p, n, sklo.p);
-                }
-                tm.end();
-            }
-            ok = build_topology(*t, s, t->root4.p, skhi.p, sklo.p, levels, tm);
-        }
-        if (!ok)
-            throw ArgError{PNBX_ERR_DEPTH,
-                           "octree deeper than 42 levels (more than leaf_capacity coincident or nearly coincident "
-                           "points); the reference would recurse without bound here"};
-        gather_sorted_soft(*t, s);
-        if (t->has_mass) build_mass_payload(*t, s, tm);  // gravity.rs:210-220
-        else gather_sorted_sources(*t, s);
-        PNBX_CUDA(cudaStreamSynchronize(s));
-        if (ex.own_stream) cudaStreamDestroy(ex.stream);
+        tree_build(*t, tm);
+        tree_publish(*t, ex);
         *out = reinterpret_cast<pnbx_tree*>(t.release());
     });
 }
 
-extern "C" int pnbx_tree_build_mass(pnbx_tree* tp, const double* mass) {
+extern "C" int pnbx_tree_build_mass_ex(pnbx_tree* tp, const double* mass, const pnbx_opts* opts) {
     return guarded([&] {
         if (!tp) throw ArgError{PNBX_ERR_ARG, "tree is NULL"};
         auto& t = *reinterpret_cast<pnbx_tree_impl*>(tp);
-        Exec ex = tree_exec(t);
-        StageTimer tm(ex.stream);
+        if (!t.replicas.empty()) {  // PNBX_DEVICES tree: host arrays only, replayed on every copy
+            if (opts && opts->mem_space == PNBX_MEM_DEVICE)
+                throw ArgError{PNBX_ERR_ARG, "a multi-device tree takes host arrays"};
+            multi_tree_for_each(t, [&](pnbx_tree_impl& r) {
+                Exec ex = make_exec_for(r.device, r.stream);
+                StageTimer tm(r.stream);
+                if (mass) { copy_into_tree(r, ex, r.mass.p, mass, (size_t)r.n); r.has_mass = true; }
+                tree_build_mass(r, tm);
+                tree_mark_ready(r);
+                PNBX_CUDA(cudaStreamSynchronize(r.stream));
+            });
+            return;
+        }
+        pnbx_opts o = tree_opts(t, opts);
+        Exec ex = make_exec(&o);
+        StageTimer tm(t.stream);
         if (mass) {
-            t.mass.alloc((size_t)std::max<int64_t>(t.n, 1), ex.stream);
-            if (t.n) PNBX_CUDA(cudaMemcpyAsync(t.mass.p, mass, (size_t)t.n * sizeof(double), cudaMemcpyHostToDevice, ex.stream));
+            if (ex.device_ptrs) stream_wait_stream(t.stream, ex.stream, ex.device);
+            copy_into_tree(t, ex, t.mass.p, mass, (size_t)t.n);
             t.has_mass = true;
         }
-        build_mass_payload(t, ex.stream, tm);
-        finish_exec(ex);
+        tree_build_mass(t, tm);
+        tree_publish(t, ex);
     });
 }
+extern "C" int pnbx_tree_build_mass(pnbx_tree* tp, const double* mass) { return pnbx_tree_build_mass_ex(tp, mass, nullptr); }
 
-extern "C" int pnbx_tree_set_softenings(pnbx_tree* tp, const double* h) {
+extern "C" int pnbx_tree_set_softenings_ex(pnbx_tree* tp, const double* h, const pnbx_opts* opts) {
     return guarded([&] {
         if (!tp) throw ArgError{PNBX_ERR_ARG, "tree is NULL"};
         auto& t = *reinterpret_cast<pnbx_tree_impl*>(tp);
-        Exec ex = tree_exec(t);
+        if (!t.replicas.empty()) {
+            if (opts && opts->mem_space == PNBX_MEM_DEVICE)
+                throw ArgError{PNBX_ERR_ARG, "a multi-device tree takes host arrays"};
+            multi_tree_for_each(t, [&](pnbx_tree_impl& r) {
+                Exec ex = make_exec_for(r.device, r.stream);
+                if (h) {
+                    if (!r.h.p) r.h.alloc((size_t)std::max<int64_t>(r.n, 1), r.stream);
+                    copy_into_tree(r, ex, r.h.p, h, (size_t)r.n);
+                    r.has_h = true;
+                    gather_sorted_soft(r, r.stream);
+                    PNBX_CUDA(cudaGetLastError());
+                } else {
+                    r.has_h = false;
+                }
+                tree_mark_ready(r);
+                PNBX_CUDA(cudaStreamSynchronize(r.stream));
+            });
+            return;
+        }
+        pnbx_opts o = tree_opts(t, opts);
+        Exec ex = make_exec(&o);
         if (h) {
-            t.h.alloc((size_t)std::max<int64_t>(t.n, 1), ex.stream);
-            if (t.n) PNBX_CUDA(cudaMemcpyAsync(t.h.p, h, (size_t)t.n * sizeof(double), cudaMemcpyHostToDevice, ex.stream));
+            if (!t.h.p) t.h.alloc((size_t)std::max<int64_t>(t.n, 1), t.stream);  // tree built without softenings
+            if (ex.device_ptrs) stream_wait_stream(t.stream, ex.stream, ex.device);
+            copy_into_tree(t, ex, t.h.p, h, (size_t)t.n);
             t.has_h = true;
-            gather_sorted_soft(t, ex.stream);
+            gather_sorted_soft(t, t.stream);
+            PNBX_CUDA(cudaGetLastError());
         } else {
             t.has_h = false;
         }
         // hmax is deliberately left as built (tree.rs:777-782 does not touch it)
-        finish_exec(ex);
+        tree_publish(t, ex);
     });
 }
+extern "C" int pnbx_tree_set_softenings(pnbx_tree* tp, const double* h) { return pnbx_tree_set_softenings_ex(tp, h, nullptr); }
 
 extern "C" int pnbx_tree_set_kernel(pnbx_tree* tp, int kernel) {
     return guarded([&] {
         if (!tp) throw ArgError{PNBX_ERR_ARG, "tree is NULL"};
         if (kernel != PNBX_KERNEL_PLUMMER && kernel != PNBX_KERNEL_SPLINE)
             throw ArgError{PNBX_ERR_ARG, "kernel must be 0 (Plummer) or 1 (CubicSplineW2)"};
-        auto& t = *reinterpret_cast<pnbx_tree_impl*>(tp);
-        if (t.kernel != kernel && t.has_payload && t.has_hmax) {  // the gate factor c depends on the kernel (kernel.rs:20-28)
-            Exec ex = tree_exec(t);
-            PNBX_LAUNCH(update_gates, nblk(t.nn), 256, 0, ex.stream, t.hmax.p, kernel == PNBX_KERNEL_SPLINE ? 1.0 : 2.8, t.nn,
-                        t.rec.p);
-            PNBX_CUDA(cudaGetLastError());
-            finish_exec(ex);
-        }
-        t.kernel = kernel;
+        auto& primary = *reinterpret_cast<pnbx_tree_impl*>(tp);
+        auto apply = [&](pnbx_tree_impl& t) {
+            if (t.kernel != kernel && t.has_payload && t.has_hmax) {  // the gate factor c depends on the kernel (kernel.rs:20-28)
+                PNBX_CUDA(cudaSetDevice(t.device));
+                PNBX_LAUNCH(update_gates, nblk(t.nn), 256, 0, t.stream, t.hmax.p, kernel == PNBX_KERNEL_SPLINE ? 1.0 : 2.8,
+                            t.nn, t.rec.p);
+                PNBX_CUDA(cudaGetLastError());
+                tree_mark_ready(t);  // stream-ordered: evaluations wait for `ready`
+            }
+            t.kernel = kernel;
+        };
+        apply(primary);
+        for (auto& r : primary.replicas) apply(*r);
     });
 }
 
 extern "C" void pnbx_tree_destroy(pnbx_tree* tp) {
     if (!tp) return;
+    DeviceGuard restore_device;
     auto* t = reinterpret_cast<pnbx_tree_impl*>(tp);
-    int cur = 0;
-    cudaGetDevice(&cur);
     cudaSetDevice(t->device);
     delete t;
-    cudaSetDevice(cur);
 }
 
 extern "C" int pnbx_tree_get_info(const pnbx_tree* tp, pnbx_tree_info* info) {
@@ -1041,8 +1221,8 @@ extern "C" int pnbx_tree_dump_topology(const pnbx_tree* tp, double* center, doub
     return guarded([&] {
         if (!tp) throw ArgError{PNBX_ERR_ARG, "tree is NULL"};
         const auto& t = *reinterpret_cast<const pnbx_tree_impl*>(tp);
-        Exec ex = tree_exec(t);
-        cudaStream_t s = ex.stream;
+        PNBX_CUDA(cudaSetDevice(t.device));
+        cudaStream_t s = t.stream;  // ordered after the build and every setter
         const size_t nn = (size_t)t.nn;
         d2h(center, t.center.p, 3 * nn, s);
         d2h(half, t.half.p, nn, s);
@@ -1069,7 +1249,6 @@ extern "C" int pnbx_tree_dump_topology(const pnbx_tree* tp, double* center, doub
         }
         if (leaf_particles)
             for (size_t k = 0; k < (size_t)t.n; ++k) leaf_particles[k] = pm[k];
-        finish_exec(ex);
     });
 }
 
@@ -1078,14 +1257,13 @@ extern "C" int pnbx_tree_dump_payload(const pnbx_tree* tp, double* mass, double*
         if (!tp) throw ArgError{PNBX_ERR_ARG, "tree is NULL"};
         const auto& t = *reinterpret_cast<const pnbx_tree_impl*>(tp);
         if (!t.has_payload) throw ArgError{PNBX_ERR_STATE, "mass payload not built; call build_mass() first"};
-        Exec ex = tree_exec(t);
+        PNBX_CUDA(cudaSetDevice(t.device));
         const size_t nn = (size_t)t.nn;
-        d2h(mass, t.nmass.p, nn, ex.stream);
-        d2h(com, t.ncom.p, 3 * nn, ex.stream);
-        if (t.has_hmax) d2h(hmax, t.hmax.p, nn, ex.stream);
-        d2h(moments, t.moments.p, nn * t.n_moments, ex.stream);
-        PNBX_CUDA(cudaStreamSynchronize(ex.stream));
-        finish_exec(ex);
+        d2h(mass, t.nmass.p, nn, t.stream);
+        d2h(com, t.ncom.p, 3 * nn, t.stream);
+        if (t.has_hmax) d2h(hmax, t.hmax.p, nn, t.stream);
+        d2h(moments, t.moments.p, nn * t.n_moments, t.stream);
+        PNBX_CUDA(cudaStreamSynchronize(t.stream));
     });
 }
 
@@ -1093,10 +1271,10 @@ extern "C" int pnbx_tree_dump_keys(const pnbx_tree* tp, uint64_t* key_hi, uint64
     return guarded([&] {
         if (!tp) throw ArgError{PNBX_ERR_ARG, "tree is NULL"};
         const auto& t = *reinterpret_cast<const pnbx_tree_impl*>(tp);
-        Exec ex = tree_exec(t);
-        d2h(key_hi, t.key_hi.p, (size_t)t.n, ex.stream);
-        d2h(key_lo, t.key_lo.p, (size_t)t.n, ex.stream);
-        PNBX_CUDA(cudaStreamSynchronize(ex.stream));
-        finish_exec(ex);
+        PNBX_CUDA(cudaSetDevice(t.device));
+        d2h(key_hi, t.key_hi.p, (size_t)t.n, t.stream);
+        if (t.key_lo.p) d2h(key_lo, t.key_lo.p, (size_t)t.n, t.stream);
+        else if (key_lo) memset(key_lo, 0, (size_t)t.n * sizeof(uint64_t));  // 21 levels were enough: no second word
+        PNBX_CUDA(cudaStreamSynchronize(t.stream));
     });
 }

@@ -63,6 +63,7 @@ struct WalkArgs {
     int kernel;               // PNBX_KERNEL_PLUMMER | PNBX_KERNEL_SPLINE
     double* out_pot;
     double* out_acc;
+    OutSlices slices;         // multi-device self evaluation: results go to the owner of the ORIGINAL index (peer stores)
 };
 
 template <class T>
@@ -384,9 +385,19 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
         return;
     }
     if (valid) {
-        if (WANT & PNBX_WANT_POT) a.out_pot[oslot] = P;
+        double* op = a.out_pot;
+        double* oa = a.out_acc;
+        if (a.slices.n > 0) {  // the slice (a peer GPU's memory, or ours) that owns this particle's original index
+            const int64_t gi = (int64_t)a.perm[skip];
+            int o = 0;
+            while (o + 1 < a.slices.n && gi >= a.slices.bounds[o + 1]) ++o;
+            oslot = gi - a.slices.bounds[o];
+            op = a.slices.pot[o];
+            oa = a.slices.acc[o];
+        }
+        if (WANT & PNBX_WANT_POT) op[oslot] = P;
         if (WANT & PNBX_WANT_ACC) {
-            a.out_acc[3 * oslot] = Ax; a.out_acc[3 * oslot + 1] = Ay; a.out_acc[3 * oslot + 2] = Az;
+            oa[3 * oslot] = Ax; oa[3 * oslot + 1] = Ay; oa[3 * oslot + 2] = Az;
         }
     }
 }
@@ -440,7 +451,8 @@ inline unsigned nb(int64_t n) { return (unsigned)std::max<int64_t>(1, ceil_div(n
 }  // namespace
 
 void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int64_t m, int64_t tgt_begin, double theta,
-               int want, double* d_pot, double* d_acc, StageTimer& tm, unsigned long long* d_counters) {
+               int want, double* d_pot, double* d_acc, StageTimer& tm, unsigned long long* d_counters,
+               const OutSlices* slices) {
     cudaStream_t s = ex.stream;
     const bool self = d_tgt == nullptr;
     DevBuf<uint32_t> tlist, torder;
@@ -497,6 +509,7 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         a.rc = t.root4.p;
         a.kernel = t.kernel;
         a.out_pot = d_pot; a.out_acc = d_acc;
+        a.slices = slices ? *slices : OutSlices{};
     };
     const int order = std::max(1, t.order);  // order 0 and 1 are both monopoles
     tm.begin("octree.walk");
@@ -548,6 +561,11 @@ extern "C" int pnbx_tree_eval(pnbx_tree* tp, const double* tgt_pos, int64_t m, i
             throw ArgError{PNBX_ERR_ARG, "target shard outside [0, N)"};
         }
         if (m >= ((int64_t)1 << 31) - 16) throw ArgError{PNBX_ERR_ARG, "M must be < 2^31"};
+        // PNBX_DEVICES tree, whole-array host call without an explicit device: all GPUs (multi.cu)
+        if (!t.replicas.empty() && m > 0 && (!opts || (opts->mem_space == PNBX_MEM_HOST && opts->device < 0 &&
+                                                        !(opts->flags & PNBX_FLAG_TREE_ORDER))) &&
+            (!self || (tgt_begin == 0 && m == t.n)) && multi_tree_eval(t, tgt_pos, m, theta, want, out_pot, out_acc, opts))
+            return;
         pnbx_opts o = opts ? *opts : pnbx_opts{-1, PNBX_MEM_HOST, 0, 0, nullptr};
         if (o.device < 0) o.device = t.device;
         if (o.device != t.device) throw ArgError{PNBX_ERR_ARG, "tree lives on a different device"};
@@ -559,7 +577,9 @@ extern "C" int pnbx_tree_eval(pnbx_tree* tp, const double* tgt_pos, int64_t m, i
         if (want & PNBX_WANT_ACC) o_acc.bind(out_acc, (size_t)3 * m, ex);
         InArray<double> i_tgt;
         if (!self) i_tgt.bind(tgt_pos, (size_t)3 * m, ex);
+        tree_begin_use(t, ex.stream);
         tree_walk(t, ex, self ? nullptr : i_tgt.d, m, tgt_begin, theta, want, o_pot.d, o_acc.d, tm, nullptr);
+        tree_end_use(t, ex.stream);
         o_pot.finish(ex);
         o_acc.finish(ex);
         finish_exec(ex);
@@ -586,7 +606,9 @@ extern "C" int pnbx_tree_walk_counters(pnbx_tree* tp, const double* tgt_pos, int
         PNBX_CUDA(cudaMemsetAsync(cnt.p, 0, 5 * sizeof(unsigned long long), ex.stream));
         InArray<double> i_tgt;
         if (!self) i_tgt.bind(tgt_pos, (size_t)3 * m, ex);
+        tree_begin_use(t, ex.stream);
         if (m > 0) tree_walk(t, ex, self ? nullptr : i_tgt.d, m, tgt_begin, theta, 1, nullptr, nullptr, tm, cnt.p);
+        tree_end_use(t, ex.stream);
         unsigned long long h[5];
         PNBX_CUDA(cudaMemcpyAsync(h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, ex.stream));
         PNBX_CUDA(cudaStreamSynchronize(ex.stream));
@@ -623,9 +645,11 @@ extern "C" int pnbx_tree_get_order(const pnbx_tree* tp, int64_t begin, int64_t m
         if (m > 0) {
             OutArray<int64_t> oa;
             oa.bind(out, (size_t)m, ex);
+            tree_begin_use(t, ex.stream);
             PNBX_LAUNCH(perm_to_i64, (unsigned)ceil_div(m, 256), 256, 0, ex.stream, t.perm.p, begin, m,
                         ex.block_cyclic ? ex.shard_block : (int64_t)0, ex.shard_rank, ex.shard_world, oa.d);
             PNBX_CUDA(cudaGetLastError());
+            tree_end_use(t, ex.stream);
             oa.finish(ex);
         }
         finish_exec(ex);
