@@ -10,6 +10,11 @@ direct.rs:443-524), fp32 interaction arithmetic checked against the float64 orac
   torchrun --nproc-per-node N ... bench.py --gpus N ...     (one rank per GPU, targets sharded)
 
 One JSON line on stdout (rank 0). See DESIGN.md §Measurement for every key.
+
+N > 1 (torchrun): `value` = device-resident, one rank per GPU, sources replicated by one NCCL all-gather, targets
+sharded; `e2e` = rank 0 alone calls the UNCHANGED host API (Gravity(...).direct_accelerations(), pageable numpy
+arrays) with PNBX_DEVICES = all N GPUs while the other ranks wait at a host barrier; the tree_1e8 section
+(BASELINE configs 4 and 5: zoom set N = 1e8, 1e6 grid targets) runs for N >= 2 with in-run parity checks.
 """
 from __future__ import annotations
 
@@ -29,6 +34,7 @@ for p in (os.path.join(ROOT, "pynbody-extras_b200"), ROOT):
 
 import numpy as np  # noqa: E402
 
+BUILD_TRAFFIC_1E7 = None  # dram bytes of one N=1e7 build from profiles/ (filled once captured)
 FLOP_PER_INTERACTION = 20.0  # GPU-Gems-3 convention for an acceleration interaction
 EPS = 0.01
 METRIC = "direct_sum_ginteractions_per_s"
@@ -136,6 +142,37 @@ def cpu_reference_rate(pos, mass, target_seconds=12.0):
     return m * n / dt, cores, f"{m} of {n} targets (evenly strided), all {n} sources, at-points kernel path, {dt:.1f} s"
 
 
+def oracle_build_info():
+    """How the CPU port was compiled (so the GPU/CPU ratio is interpretable)."""
+    flags = "-O2 -std=c++17 -fopenmp -ffp-contract=off (oracle/Makefile; no -march=native: the reference's release "\
+            "profile does not set target-cpu either)"
+    try:
+        cxx = subprocess.run(["/usr/bin/g++", "--version"], capture_output=True, text=True).stdout.splitlines()[0]
+    except Exception:
+        cxx = "g++ (version unavailable)"
+    return {"compiler": cxx, "flags": flags}
+
+
+def real_reference():
+    """use the real Rust extension the day it exists — baseline/_ref (a pip --target install of the
+    reference) or an importable pynbodyext._rust that is NOT our ctypes shim. Returns the module or None."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(ref_dir):
+        return None
+    import importlib.util
+    for root, _dirs, files in os.walk(ref_dir):
+        for f in files:
+            if f.startswith("_rust") and f.endswith(".so"):
+                try:
+                    spec = importlib.util.spec_from_file_location("pynbodyext_ref_rust", os.path.join(root, f))
+                    mod = importlib.util.module_from_spec(spec)
+                    spec.loader.exec_module(mod)
+                    return mod
+                except Exception:
+                    return None
+    return None
+
+
 def tree_section(args, rank, world, local, dev, barrier, peak_tf):
     """Secondary metric of BASELINE.json: tree gravity particles/s on config 3 (NFW halo + exponential disc,
     per-particle spline softening, theta 0.7, order 3, leaf 8; bench_gravity.py shape = construct + potentials).
@@ -213,45 +250,251 @@ def tree_section(args, rank, world, local, dev, barrier, peak_tf):
                           "pnbx_tree_walk_counters (== oracle counters)",
             "interactions_per_s": (cnt["accepts"] + cnt["leaf_particles"]) / (k_acc_ms * 1e-3),
             "traffic": 1.448e9 if (world == 1 and n == 10_000_000) else None,
-            "traffic_note": "dram read+write of one N=1e7 potentials launch from ncu --set full "
-                            "(profiles/r01_walk_kernel_ncu.md, final capture); the kernel is issue bound, not HBM bound",
+            "traffic_source": "from_profile",
+            "traffic_note": "dram read+write of one N=1e7 potentials launch from ncu --set full (profiles/, walk kernel "
+                            "summary; not re-measured in this run); the kernel is issue bound, not HBM bound",
         },
         "roofline_build": {
             "bound": "hbm", "unit": "GB/s", "achieved": 0.53e3 * n / (build_ms * 1e-3) / 1e9,
-            "peak": peaks().get("hbm_gbs", 6650.0), "traffic": None,
+            "peak": peaks().get("hbm_gbs", 6650.0), "traffic": BUILD_TRAFFIC_1E7 if n == 10_000_000 else None,
+            "traffic_source": "from_profile",
             "frac": 0.53e3 * n / (build_ms * 1e-3) / 1e9 / peaks().get("hbm_gbs", 6650.0),
             "algorithmic_bytes_per_particle": 530,
         },
     }
     if rank == 0 and world == 1:
-        # e2e through the drop-in API with host arrays (H2D of 40 B/particle and D2H inside the timed region)
+        # e2e through the drop-in API with HOST arrays (H2D of 40 B/particle and D2H inside the timed region): ordinary
+        # pageable numpy arrays are the headline (what a caller holds), pinned arrays the second number
         def pin(a):
             return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-        pos_h, mass_h, h_h = pin(pos), pin(mass), pin(h)
-        for _ in range(2):  # warm-up; one tree alive at a time, like a user holding one Gravity object
-            g = Gravity(pos_h, mass_h, softening=h_h, kernel=KernelKind.Spline)
-            g.tree_potentials(theta=theta)
-            del g
-        reps = 3
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            ta = time.perf_counter()
-            g = Gravity(pos_h, mass_h, softening=h_h, kernel=KernelKind.Spline)
-            _ = g.tree
-            tb = time.perf_counter()
-            out = g.tree_potentials(theta=theta)
-            tc = time.perf_counter()
-            del g
-            print(f"[bench] tree e2e: construct {1e3 * (tb - ta):.1f} ms, potentials {1e3 * (tc - tb):.1f} ms, "
-                  f"free {1e3 * (time.perf_counter() - tc):.1f} ms", file=sys.stderr)
-        dt = (time.perf_counter() - t0) / reps
-        res["e2e"] = {"value": n / dt, "unit": "particles/s", "ms_per_step": dt * 1e3,
-                      "h2d_bytes_per_step": int(pos.nbytes + mass.nbytes + h.nbytes), "d2h_bytes_per_step": int(out.nbytes),
-                      "api": "Gravity(pos, mass, softening=h, kernel=Spline).tree_potentials(theta=0.7) (construct + walk), "
-                             "pinned host arrays"}
+
+        def e2e_run(pos_h, mass_h, h_h, label):
+            for _ in range(2):  # warm-up; one tree alive at a time, like a user holding one Gravity object
+                g = Gravity(pos_h, mass_h, softening=h_h, kernel=KernelKind.Spline)
+                g.tree_potentials(theta=theta)
+                del g
+            reps = 3
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                ta = time.perf_counter()
+                g = Gravity(pos_h, mass_h, softening=h_h, kernel=KernelKind.Spline)
+                _ = g.tree
+                tb = time.perf_counter()
+                out = g.tree_potentials(theta=theta)
+                tc = time.perf_counter()
+                del g
+                print(f"[bench] tree e2e ({label}): construct {1e3 * (tb - ta):.1f} ms, potentials {1e3 * (tc - tb):.1f} ms, "
+                      f"free {1e3 * (time.perf_counter() - tc):.1f} ms", file=sys.stderr)
+            dt = (time.perf_counter() - t0) / reps
+            return {"value": n / dt, "unit": "particles/s", "ms_per_step": dt * 1e3,
+                    "h2d_bytes_per_step": int(pos.nbytes + mass.nbytes + h.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+                    "api": "Gravity(pos, mass, softening=h, kernel=Spline).tree_potentials(theta=0.7) (construct + walk), "
+                           + label}
+        res["e2e"] = e2e_run(pos, mass, h, "pageable numpy arrays")
+        res["e2e_pinned"] = e2e_run(pin(pos), pin(mass), pin(h), "pinned host arrays")
     del tree
     return res
+
+
+def tree_1e8_section(args, rank, world, local, dev, barrier, gloo, peak_tf):
+    """BASELINE configs 4 and 5: dm/gas/star zoom set N = 1e8 (deterministic zoom_range: the same global set at any
+    world size), spline softening, theta 0.7, order 3, leaf 8, sharded over the GPUs of the box; 1e6 (R,z) grid targets
+    from the same sources. Device-timed stages (max over ranks), end to end from pinned host shards to pinned host
+    results, with IN-RUN parity: fp32 vs float64 walk on 1e4 self targets (same interaction lists) <= 1e-5, and tree
+    (float64) vs float64 DIRECT sum at 1e4 particle positions and at 1e4 grid points within the theta = 0.7
+    truncation bound. Then the same workload through the unchanged host API from ONE process (PNBX_DEVICES)."""
+    import torch
+    import torch.distributed as dist
+
+    from benchmarks.synthetic import rz_grid_targets, zoom_range
+    from pynbodyext.gravity import device as gdev
+    from pynbodyext.gravity.sharded import pack_shard, replicate_sources, shard_bounds
+
+    n, theta, order, leaf = args.tree1e8_n, 0.7, 3, 8
+    b = shard_bounds(n, world)
+    lo, hi = b[rank], b[rank + 1]
+    per = max(b[r + 1] - b[r] for r in range(world))
+    t0 = time.perf_counter()
+    pos, mass, h, _fam = zoom_range(n, lo, hi, seed=4)
+    rows_h = torch.from_numpy(pack_shard(pos, mass, h, 0, hi - lo, per)).pin_memory()
+    gen_s = time.perf_counter() - t0
+
+    def stage(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), r
+
+    m_r = gdev.shard_count(n, world, rank)
+    cap = per + gdev.SHARD_BLOCK
+    pot_h = torch.empty(cap, dtype=torch.float64).pin_memory()
+    acc_h = torch.empty((cap, 3), dtype=torch.float64).pin_memory()
+    idx_h = torch.empty(cap, dtype=torch.int64).pin_memory()
+    best = None
+    tree = d_pos = d_mass = d_h = None
+    for rep in range(2):
+        del tree, d_pos, d_mass, d_h
+        t_h2d, rows = stage(lambda: rows_h.to(dev, non_blocking=True))
+        t_gather, allrows = stage(lambda: replicate_sources(rows, b))
+        t_split, (d_pos, d_mass, d_h) = stage(lambda: (allrows[:, 0:3].contiguous(), allrows[:, 3].contiguous(),
+                                                       allrows[:, 4].contiguous()))
+        del allrows, rows
+        t_build, tree = stage(lambda: gdev.OctreeDevice(d_pos, d_mass, leaf, order, d_h, 1))
+        t_pot, pot = stage(lambda: tree.eval(theta, 1, shard=(rank, world), kernel_events=True)[0])
+        k_pot = gdev.last_kernel_ms()
+        t_acc, acc = stage(lambda: tree.eval(theta, 2, shard=(rank, world), kernel_events=True)[1])
+        k_acc = gdev.last_kernel_ms()
+        t_d2h, _ = stage(lambda: (pot_h[:m_r].copy_(pot, non_blocking=True), acc_h[:m_r].copy_(acc, non_blocking=True),
+                                  idx_h[:m_r].copy_(tree.order(shard=(rank, world)), non_blocking=True)))
+        res = {"h2d_ms": t_h2d, "allgather_ms": t_gather, "unpack_ms": t_split, "build_ms": t_build, "walk_pot_ms": t_pot,
+               "walk_acc_ms": t_acc, "d2h_ms": t_d2h, "walk_pot_kernel_ms": k_pot, "walk_acc_kernel_ms": k_acc}
+        res["total_pot_ms"] = t_h2d + t_gather + t_split + t_build + t_pot
+        res["total_ms"] = res["total_pot_ms"] + t_acc + t_d2h
+        if best is None or res["total_ms"] < best["total_ms"]:
+            best = res
+        finite = bool(torch.isfinite(pot).all() and torch.isfinite(acc).all())
+        del pot, acc
+    info = tree.info()
+    cnt = tree.walk_counters(theta, shard=(rank, world))
+    tcnt = torch.tensor([cnt[k] for k in ("visits", "accepts", "leaf_visits", "leaf_particles")], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tcnt)
+    visits, accepts, leaf_visits, leaf_pairs = (float(x) for x in tcnt)
+    flop_acc = accepts * 140.0 + leaf_pairs * 20.0 + visits * 10.0
+
+    def rms(x):
+        return float(x.pow(2).mean().sqrt())
+
+    # ---- check 1 (rank 0's copy of the tree): fp32 vs float64 arithmetic on the same interaction lists
+    c_lo, c_n = n // 2, 10_000
+    p32, a32 = tree.eval(theta, 3, tgt_begin=c_lo, count=c_n)
+    p64, a64 = tree.eval(theta, 3, tgt_begin=c_lo, count=c_n, precision="f64")
+    chk_fp = {"rms_rel_pot": rms((p32 - p64) / p64), "rms_rel_acc": rms((a32 - a64).norm(dim=1) / a64.norm(dim=1)),
+              "targets": c_n, "tolerance": 1e-5}
+    chk_fp["ok"] = bool(chk_fp["rms_rel_pot"] < 1e-5 and chk_fp["rms_rel_acc"] < 1e-5)
+
+    # ---- check 2: tree (f64) vs float64 direct sum, at-points, targets sharded over the ranks
+    def tree_vs_direct(q_all):
+        qb = shard_bounds(q_all.shape[0], world)
+        q = q_all[qb[rank]:qb[rank + 1]].contiguous()
+        pt = tree.eval(theta, 1, targets=q, precision="f64")[0]
+        pd = gdev.direct_device(d_pos, d_mass, d_h, kernel=1, want=1, targets=q, precision="f64")[0]
+        err = ((pt - pd) / pd).abs()
+        if world > 1:
+            parts = [torch.empty(qb[r + 1] - qb[r], dtype=torch.float64, device=dev) for r in range(world)]
+            dist.all_gather(parts, err)
+            err = torch.cat(parts)
+        out = {"targets": int(err.numel()), "median": float(err.median()), "p90": float(err.quantile(0.9)), "max": float(err.max()),
+               "bound": "median < 2e-4 and max < 1e-2 (theta 0.7, order 3; single_node.rs far-field bound 1e-2)"}
+        out["ok"] = bool(out["median"] < 2e-4 and out["max"] < 1e-2)
+        return out
+
+    chk_self = tree_vs_direct(d_pos[c_lo:c_lo + c_n])
+
+    # ---- config 5: 1e6 grid targets, target-sharded
+    grid = rz_grid_targets(args.grid_targets, seed=5)
+    gb = shard_bounds(grid.shape[0], world)
+    g_h = torch.from_numpy(np.ascontiguousarray(grid[gb[rank]:gb[rank + 1]])).pin_memory()
+    gp_h = torch.empty(gb[rank + 1] - gb[rank], dtype=torch.float64).pin_memory()
+
+    def grid_e2e():
+        d_t = g_h.to(dev, non_blocking=True)
+        gp = tree.eval(theta, 1, targets=d_t, kernel_events=True)[0]
+        gp_h.copy_(gp, non_blocking=True)
+        return gp
+
+    grid_e2e()
+    t_grid, gp = stage(grid_e2e)
+    k_grid = gdev.last_kernel_ms()
+    chk_grid = tree_vs_direct(torch.from_numpy(np.ascontiguousarray(grid[::100])).to(dev))
+    out = None
+    if rank == 0:
+        out = {
+            "workload": f"dm/gas/star zoom set N={n} (zoom_range seed 4, identical at every world size), spline "
+                        f"softening (gas h ∝ spacing), theta={theta}, order={order}, leaf={leaf}; BASELINE.json configs[3]; "
+                        f"grid: {grid.shape[0]} log-spaced (R,z) targets (configs[4])",
+            "n_gpus": world, "n": n, "nodes": info["n_nodes"], "depth": info["depth"], "finite": finite,
+            "host_generate_s_per_rank": gen_s, **best,
+            "particles_per_s": n / (best["total_ms"] * 1e-3),
+            "value": n / (best["total_ms"] * 1e-3), "unit": "particles/s",
+            "metric": "tree_particles_per_s (pinned host shards -> potentials + accelerations in pinned host memory)",
+            "e2e": {"value": n / (best["total_ms"] * 1e-3), "unit": "particles/s",
+                    "h2d_bytes_per_step": int(n * 40), "d2h_bytes_per_step": int(n * 40),
+                    "api": "one process per GPU: shard H2D + NCCL all-gather + build + block-cyclic walk + D2H "
+                           "(pynbodyext.gravity.device / sharded)"},
+            "per_target": {"visits": visits / n, "accepts": accepts / n, "leaf_visits": leaf_visits / n, "leaf_pairs": leaf_pairs / n},
+            "roofline": {"bound": "fp32", "kernel": "walk_kernel<3,acc,f32,spline>", "unit": "TFLOP/s",
+                         "achieved": flop_acc / world / (best["walk_acc_kernel_ms"] * 1e-3) / 1e12, "peak": peak_tf,
+                         "frac": flop_acc / world / (best["walk_acc_kernel_ms"] * 1e-3) / 1e12 / peak_tf,
+                         "work_model": "per GPU: accepts*140 + leaf_pairs*20 + visits*10 flop (BASELINE.md §3), counts summed "
+                                       "over ranks / world", "traffic": None},
+            "roofline_build": {"bound": "hbm", "unit": "GB/s", "achieved": 0.53e3 * n / (best["build_ms"] * 1e-3) / 1e9,
+                               "peak": peaks().get("hbm_gbs", 6650.0),
+                               "frac": 0.53e3 * n / (best["build_ms"] * 1e-3) / 1e9 / peaks().get("hbm_gbs", 6650.0),
+                               "note": "replicated build: every GPU builds the whole tree"},
+            "checks": {"fp32_vs_f64_same_lists": chk_fp, "tree_vs_direct_f64_particle_positions": chk_self,
+                       "tree_vs_direct_f64_grid_points": chk_grid,
+                       "all_ok": bool(chk_fp["ok"] and chk_self["ok"] and chk_grid["ok"])},
+            "grid": {"targets": int(grid.shape[0]), "e2e_ms": t_grid, "walk_kernel_ms": k_grid,
+                     "targets_per_s": grid.shape[0] / (t_grid * 1e-3),
+                     "api": "pinned host targets -> H2D -> tree.eval(targets) -> pinned host potentials, target-sharded"},
+        }
+    del tree, d_pos, d_mass, d_h, gp
+    torch.cuda.empty_cache()
+    gdev.trim_memory()  # hand the library's cached blocks back before another process builds the same tree on this GPU
+
+    # ---- the same workload through the UNCHANGED host API from one process (rank 0 drives all GPUs, PNBX_DEVICES)
+    if world > 1 and not args.no_api_1e8:
+        full = []
+        for a in (pos, mass, h):  # gather the per-rank shards of the host arrays on rank 0 (gloo, equal padded sizes)
+            pad = np.zeros((per,) + a.shape[1:])
+            pad[:hi - lo] = a
+            t_sh = torch.from_numpy(pad)
+            if rank == 0:
+                parts = [torch.empty_like(t_sh) for _ in range(world)]
+                dist.gather(t_sh, parts, dst=0, group=gloo)
+                full.append(np.concatenate([parts[r].numpy()[:b[r + 1] - b[r]] for r in range(world)]))
+                del parts
+            else:
+                dist.gather(t_sh, None, dst=0, group=gloo)
+        if rank == 0:
+            from pynbodyext.gravity import Gravity, KernelKind
+            os.environ["PNBX_DEVICES"] = ",".join(str(i) for i in range(world))
+            try:
+                fpos, fmass, fh = full
+                ms = []
+                for rep in range(2):
+                    ta = time.perf_counter()
+                    g = Gravity(fpos, fmass, softening=fh, kernel=KernelKind.Spline)
+                    _ = g.tree
+                    tb = time.perf_counter()
+                    p_api = g.tree_potentials(theta=theta)
+                    tc = time.perf_counter()
+                    a_api = g.tree_accelerations(theta=theta)
+                    td = time.perf_counter()
+                    del g
+                    ms.append({"construct_ms": 1e3 * (tb - ta), "potentials_ms": 1e3 * (tc - tb),
+                               "accelerations_ms": 1e3 * (td - tc), "total_ms": 1e3 * (td - ta)})
+                bapi = min(ms, key=lambda x: x["total_ms"])
+                same = bool(np.array_equal(p_api[c_lo:c_lo + c_n], p32.cpu().numpy()))
+                out["api_e2e"] = {**bapi, "value": n / (bapi["total_ms"] * 1e-3), "unit": "particles/s",
+                                  "h2d_bytes_per_step": int(n * 40), "d2h_bytes_per_step": int(n * 32),
+                                  "finite": bool(np.isfinite(p_api).all() and np.isfinite(a_api).all()),
+                                  "bit_equal_to_sharded_run_on_check_targets": same,
+                                  "api": "Gravity(pos, mass, softening=h, kernel=Spline): .tree (construct), "
+                                         ".tree_potentials(), .tree_accelerations() — pageable numpy arrays, one process, "
+                                         f"PNBX_DEVICES={os.environ['PNBX_DEVICES']}"}
+            finally:
+                os.environ.pop("PNBX_DEVICES", None)
+        dist.barrier(group=gloo)
+    return out
 
 
 def tree_cpu_baseline(args):
@@ -281,24 +524,40 @@ def run_reference(args):
         return
     from benchmarks.synthetic import hernquist
     pos, mass = hernquist(args.n, seed=2)
-    rates = []
+    n_int = args.n * (args.n - 1)
+    ref = real_reference()
     per_step = max(2.0, min(12.0, 60.0 / max(1, args.steps + args.warmup)))
+    rates = []
     sample = ""
     cores = 1
+    kind = "port"
+    note = ("CPU oracle (C++/OpenMP port of direct.rs; no Rust toolchain in this image, baseline/_ref absent); "
+            "ms_per_step extrapolated from the sampled rate to the full N(N-1) interactions")
     for i in range(args.warmup + args.steps):
-        r, cores, sample = cpu_reference_rate(pos, mass, per_step)
+        if ref is not None:  # the real Rust extension (gravity.rs:514-582): same bounded at-points sample
+            kind = "reference"
+            cores = len(os.sched_getaffinity(0))
+            m = max(512, min(args.n, int(2.0e8 * cores * per_step / args.n)))
+            idx = np.linspace(0, args.n - 1, m).astype(np.int64)
+            h = np.full(args.n, EPS)
+            t0 = time.perf_counter()
+            ref.direct_accelerations_at_points_py(pos, np.ascontiguousarray(pos[idx]), mass, 0, h, 0)
+            dt = time.perf_counter() - t0
+            r, sample = m * args.n / dt, f"{m} of {args.n} targets (evenly strided), all sources, pynbodyext._rust from baseline/_ref, {dt:.1f} s"
+            note = "the reference's own Rust extension (baseline/_ref), rayon on all host cores"
+        else:
+            r, cores, sample = cpu_reference_rate(pos, mass, per_step)
         if i >= args.warmup:
             rates.append(r)
     v = float(np.mean(rates)) / 1e9
-    n_int = args.n * (args.n - 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": n_int / (v * 1e9) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.n, args.gpus),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, **oracle_build_info()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU oracle (C++/OpenMP port of direct.rs; Rust toolchain absent); ms_per_step extrapolated "
-                "from the sampled rate to the full N(N-1) interactions",
+        "parity_pin": "oracle-only" if ref is None else "reference",
+        "note": note,
     }
     emit(line)
 
@@ -318,8 +577,10 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        gloo = dist.new_group(backend="gloo")  # host-side barrier / gathers: waiting ranks must not spin on their GPUs
     n = args.n
     pos, mass = hernquist(n, seed=2)
 
@@ -355,8 +616,6 @@ def run_ours(args):
             rows = torch.cat([d_all[r * per: r * per + (bounds[r + 1] - bounds[r])] for r in range(world)])
         return rows[:, 0:3].contiguous(), rows[:, 3].contiguous(), rows[:, 4].contiguous()
 
-    kernel_ms = []
-
     def step(record=False):
         p, m_, h_ = gather_sources()
         _, acc = gdev.direct_device(p, m_, h_, kernel=0, want=2, tgt_begin=lo, count=cnt, kernel_events=record)
@@ -379,7 +638,6 @@ def run_ours(args):
     ev[0].record()
     for _ in range(args.steps):
         acc = step(record=True)
-        kernel_ms.append(None)  # filled after the sync (events are read without stalling the loop)
     ev[1].record()
     barrier()
     ms_total = ev[0].elapsed_time(ev[1])
@@ -408,6 +666,18 @@ def run_ours(args):
     torch.cuda.synchronize()
     k_ms_general = gdev.last_kernel_ms()
     del os.environ["PNBX_DIRECT_NO_CONSTM"]
+    # the softened variants on the same sources (per-particle Plummer and cubic spline, h in [0.005, 0.02])
+    softened = {}
+    if world == 1 and not args.no_softened:
+        d_hv = to_dev(np.random.default_rng(0).uniform(0.005, 0.02, n))
+        for name, kern in (("plummer_pair", 0), ("spline", 1)):
+            for _ in range(2):
+                gdev.direct_device(d_pos, d_mass, d_hv, kernel=kern, want=2, kernel_events=True)
+            torch.cuda.synchronize()
+            ms_v = gdev.last_kernel_ms()
+            softened[name] = {"kernel_ms": ms_v, "achieved": FLOP_PER_INTERACTION * n_int / (ms_v * 1e-3) / 1e12,
+                              "frac": FLOP_PER_INTERACTION * n_int / (ms_v * 1e-3) / 1e12 / meas_tf}
+        del d_hv
     roofline = {
         "bound": "fp32", "kernel": "direct_kernel_f2<acc, const_mass> (packed FP32x2; the workload has equal masses)",
         "achieved": achieved_tf,
@@ -419,14 +689,14 @@ def run_ours(args):
         "general_mass_variant": {"kernel_ms": k_ms_general,
                                  "achieved": FLOP_PER_INTERACTION * int_per_launch / (k_ms_general * 1e-3) / 1e12,
                                  "frac": FLOP_PER_INTERACTION * int_per_launch / (k_ms_general * 1e-3) / 1e12 / meas_tf},
-        "traffic": 172.3e6,
-        "traffic_note": "dram read+write per 1e12-interaction launch from ncu --set full (profiles/r01_direct_kernel_f2_ncu.md); "
-                        "algorithmic HBM bytes ~ 16 B per source per launch + 24 B per target result",
+        "softened_variants": softened or None,
+        "traffic": 172.3e6, "traffic_source": "from_profile",
+        "traffic_note": "dram read+write per 1e12-interaction launch from ncu --set full (profiles/, direct kernel summary; "
+                        "not re-measured in this run); algorithmic HBM bytes ~ 16 B per source per launch + 24 B per target result",
     }
 
     # ---- parity in the same run: fp32 GPU vs float64 oracle on a 256-target subsample (rank 0)
     parity = None
-    e2e = None
     cpu = None
     if rank == 0:
         from oracle import oracle as O
@@ -437,44 +707,79 @@ def run_ours(args):
         parity = {"rms_rel_acc_vs_f64_oracle": float(np.sqrt((((a_gpu - a_ref) ** 2).sum(1) / (a_ref ** 2).sum(1)).mean())),
                   "targets": 256, "tolerance": 1e-5}
 
-    # ---- e2e through the public drop-in API with pinned HOST buffers (H2D + D2H inside the timed region)
+    # ---- e2e through the public drop-in API with HOST buffers (H2D + D2H inside the timed region).
+    # Headline: ordinary pageable numpy arrays, Gravity(...).direct_accelerations(). N > 1: the same call from rank 0
+    # alone with PNBX_DEVICES = all N GPUs (one host thread per GPU inside the library); the other ranks wait.
     def pinned(a):
-        tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return tt.numpy()
-    pos_h, mass_h = pinned(pos), pinned(mass)
-    import pynbodyext._rust as backend
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
 
-    def e2e_step():
-        if world == 1:
-            g = Gravity(pos_h, mass_h, softening=EPS, kernel=KernelKind.Plummer)
-            return g.direct_accelerations()
+    def time_api(pos_h, mass_h, e_steps):
+        def call():
+            return Gravity(pos_h, mass_h, softening=EPS, kernel=KernelKind.Plummer).direct_accelerations()
+        call()
+        call()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            out = call()
+        return (time.perf_counter() - t0) / e_steps, out
+
+    e_steps = max(1, min(args.steps, 5))
+    e2e = None
+    e2e_extra = {}
+    if world == 1:
+        dt, out = time_api(pos, mass, e_steps)
+        dt_pin, _ = time_api(pinned(pos), pinned(mass), e_steps)
+        e2e = {"value": n_int / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(pos.nbytes + mass.nbytes + h_full.nbytes),
+               "d2h_bytes_per_step": int(out.nbytes), "ms_per_step": dt * 1e3, "steps": e_steps,
+               "api": "Gravity(pos, mass, softening=0.01, kernel=Plummer).direct_accelerations(), pageable numpy arrays"}
+        e2e_extra["e2e_pinned"] = {"value": n_int / dt_pin / 1e9, "unit": UNIT, "ms_per_step": dt_pin * 1e3,
+                                   "api": "the same call with pinned host arrays"}
+    else:
+        barrier()
+        if rank == 0:
+            os.environ["PNBX_DEVICES"] = ",".join(str(i) for i in range(world))
+            try:
+                dt, out = time_api(pos, mass, e_steps)
+            finally:
+                os.environ.pop("PNBX_DEVICES", None)
+            e2e = {"value": n_int / dt / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": int(pos.nbytes + mass.nbytes + h_full.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+                   "ms_per_step": dt * 1e3, "steps": e_steps,
+                   "api": "Gravity(pos, mass, softening=0.01, kernel=Plummer).direct_accelerations(), pageable numpy arrays, "
+                          f"ONE process driving {world} GPUs (PNBX_DEVICES; per-GPU shard H2D, peer all-gather over NVLink, "
+                          "per-GPU D2H into the caller's array); the other ranks idle at a host barrier"}
+        dist.barrier(group=gloo)
+        # second number: one process per GPU through the torch.distributed helper (per-rank shard H2D, NCCL all-gather)
         from pynbodyext.gravity.sharded import direct_sharded
-        return direct_sharded(pos_h, mass_h, h_full, kernel=0, want=2, rank=rank, world=world, device=local)[1]
 
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e_steps = max(1, min(args.steps, 3))
-    for _ in range(e_steps):
-        out = e2e_step()
-    barrier()
-    e_dt = torch.tensor([(time.perf_counter() - t0) / e_steps], dtype=torch.float64, device=dev)
-    if world > 1:
+        def sharded_step():
+            return direct_sharded(pos, mass, h_full, kernel=0, want=2, rank=rank, world=world, device=local)[1]
+        sharded_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            sharded_step()
+        barrier()
+        e_dt = torch.tensor([(time.perf_counter() - t0) / e_steps], dtype=torch.float64, device=dev)
         dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
-    e2e = {"value": n_int / float(e_dt[0]) / 1e9, "unit": UNIT,
-           "h2d_bytes_per_step": int(pos.nbytes + mass.nbytes + h_full.nbytes) if world == 1 else int(cnt * 40),
-           "d2h_bytes_per_step": int(cnt * 24), "ms_per_step": float(e_dt[0]) * 1e3, "steps": e_steps,
-           "api": "Gravity(...).direct_accelerations() with pinned host numpy arrays" if world == 1
-                  else "pynbodyext.gravity.sharded.direct_sharded (per-rank shard H2D, NCCL all-gather, D2H)"}
+        e2e_extra["e2e_one_process_per_gpu"] = {
+            "value": n_int / float(e_dt[0]) / 1e9, "unit": UNIT, "ms_per_step": float(e_dt[0]) * 1e3,
+            "api": "pynbodyext.gravity.sharded.direct_sharded (per-rank shard H2D, NCCL all-gather, D2H)"}
 
     tree = None
     if not args.no_tree:
         tree = tree_section(args, rank, world, local, dev, barrier, meas_tf)
+    tree_1e8 = None
+    if (world > 1 or args.tree1e8) and not args.no_tree1e8:
+        del d_pos, d_mass, d_h
+        torch.cuda.empty_cache()
+        tree_1e8 = tree_1e8_section(args, rank, world, local, dev, barrier, gloo, meas_tf)
 
     # CPU legs last: the oracle's OpenMP team must not compete with the host side of the GPU measurements above
     if rank == 0 and world == 1 and not args.no_cpu:
         r, cores, sample = cpu_reference_rate(pos, mass, 12.0)
-        cpu = {"value": r / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        cpu = {"value": r / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, **oracle_build_info()}
         if tree is not None:
             tree["cpu_baseline"] = tree_cpu_baseline(args)
     if rank == 0:
@@ -482,8 +787,10 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(n, world), "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
-            "tflops_20flop": FLOP_PER_INTERACTION * value * 1e9 / 1e12, "tree": tree,
+            "e2e": e2e, **e2e_extra, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
+            "parity_pin": "oracle-only (the Rust reference cannot be built in this image; the oracle is a line-by-line "
+                          "port checked by ORACLE_REVIEW.md and independent symbolic tests)",
+            "tflops_20flop": FLOP_PER_INTERACTION * value * 1e9 / 1e12, "tree": tree, "tree_1e8": tree_1e8,
         }
         emit(line)
     if world > 1:
@@ -500,6 +807,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tree", action="store_true", help="skip the secondary tree-gravity section")
     ap.add_argument("--tree-n", type=int, default=10_000_000)
+    ap.add_argument("--no-softened", action="store_true", help="skip the per-pair Plummer / spline direct kernel timings")
+    ap.add_argument("--tree1e8", action="store_true", help="run the N=1e8 zoom tree section on one GPU too")
+    ap.add_argument("--no-tree1e8", action="store_true", help="skip the N=1e8 zoom tree section (it runs by default for N > 1)")
+    ap.add_argument("--tree1e8-n", type=int, default=100_000_000)
+    ap.add_argument("--grid-targets", type=int, default=1_000_000)
+    ap.add_argument("--no-api-1e8", action="store_true", help="skip the one-process PNBX_DEVICES leg of the N=1e8 section")
     args = ap.parse_args()
     # Exactly one JSON line may reach stdout: route everything else written to fd 1 (NCCL's version banner,
     # library chatter) to stderr and keep the real stdout for the result line.

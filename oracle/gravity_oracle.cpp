@@ -1443,8 +1443,17 @@ int pnbx_oracle_tree_set_kernel(void* tp, int kernel) {  // tree.rs:784-786
 void pnbx_oracle_tree_destroy(void* tp) { delete static_cast<Octree*>(tp); }
 
 // tree.rs:1415-1558. counters (nullable): [visits, accepts, leaf_visits, leaf_particles] totals.
+// Self mode evaluates own particles [begin, begin+m) (compute_* restricted to a target range: the per-target work of
+// tree.rs:1415-1496 is independent of the other targets; begin = 0, m = N is the reference call).
+int pnbx_oracle_tree_eval_range(void* tp, const double* tgt_pos, int64_t begin, int64_t m, double theta, int want,
+                                double* out_pot, double* out_acc, int64_t* counters);
 int pnbx_oracle_tree_eval(void* tp, const double* tgt_pos, int64_t m, double theta, int want,
                           double* out_pot, double* out_acc, int64_t* counters) {
+    const Octree& t = *static_cast<Octree*>(tp);
+    return pnbx_oracle_tree_eval_range(tp, tgt_pos, 0, tgt_pos ? m : t.n(), theta, want, out_pot, out_acc, counters);
+}
+int pnbx_oracle_tree_eval_range(void* tp, const double* tgt_pos, int64_t begin, int64_t m, double theta, int want,
+                                double* out_pot, double* out_acc, int64_t* counters) {
     const Octree& t = *static_cast<Octree*>(tp);
     if (!t.has_bh) {
         g_err = "mass payload not built; call build_mass() before compute";
@@ -1452,7 +1461,11 @@ int pnbx_oracle_tree_eval(void* tp, const double* tgt_pos, int64_t m, double the
     }
     Ctx ctx = make_ctx(t, theta);
     const bool self = tgt_pos == nullptr;
-    const int64_t count = self ? t.n() : m;
+    if (self && (begin < 0 || begin + m > t.n())) {
+        g_err = "target range outside [0, N)";
+        return 1;
+    }
+    const int64_t count = m;
     int64_t tot[4] = {0, 0, 0, 0};
     for (int pass = 0; pass < 2; ++pass) {
         const bool do_pot = pass == 0;
@@ -1461,10 +1474,11 @@ int pnbx_oracle_tree_eval(void* tp, const double* tgt_pos, int64_t m, double the
         int64_t v = 0, a = 0, lv = 0, lp = 0;
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : v, a, lv, lp) if (count >= 1024)
         for (int64_t i = 0; i < count; ++i) {
-            const double* target = self ? &t.positions[3 * i] : tgt_pos + 3 * i;
-            int64_t skip = self ? i : NONE;
+            const int64_t gi = self ? begin + i : i;  // particle index of a self target
+            const double* target = self ? &t.positions[3 * gi] : tgt_pos + 3 * i;
+            int64_t skip = self ? gi : NONE;
             bool has_th = self && t.has_softenings;
-            double th = has_th ? t.softenings[i] : 0.0;
+            double th = has_th ? t.softenings[gi] : 0.0;
             Counters c;
             if (do_pot) {
                 double o = 0.0;

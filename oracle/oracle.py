@@ -49,6 +49,7 @@ def lib():
         L.pnbx_oracle_tree_destroy.argtypes = [C.c_void_p]
         L.pnbx_oracle_tree_destroy.restype = None
         L.pnbx_oracle_tree_eval.argtypes = [C.c_void_p, _d, C.c_int64, C.c_double, C.c_int, _d, _d, _i64]
+        L.pnbx_oracle_tree_eval_range.argtypes = [C.c_void_p, _d, C.c_int64, C.c_int64, C.c_double, C.c_int, _d, _d, _i64]
         L.pnbx_oracle_tree_info.argtypes = [C.c_void_p, _i64]
         L.pnbx_oracle_tree_dump_topology.argtypes = [C.c_void_p, _d, _d, _i32, _i64, _i64, _i64, _i64, _i64, _u64, _u64]
         L.pnbx_oracle_tree_dump_payload.argtypes = [C.c_void_p, _d, _d, _d, _d]
@@ -138,13 +139,15 @@ class Tree:
     def set_kernel(self, kernel=None):
         lib().pnbx_oracle_tree_set_kernel(self._h, 0 if kernel is None else int(kernel))
 
-    def eval(self, theta, targets=None, want=3, counters=False):
+    def eval(self, theta, targets=None, want=3, counters=False, begin=0, count=None):
+        """compute_* (targets=None: own particles [begin, begin+count), default all) / *_at_points."""
         targets = _f64(targets, 3)
-        m = self.n if targets is None else targets.shape[0]
+        m = (self.n - begin if count is None else int(count)) if targets is None else targets.shape[0]
         pot = np.empty(m) if want & 1 else None
         acc = np.empty((m, 3)) if want & 2 else None
         cnt = np.zeros(4, dtype=np.int64) if counters else None
-        rc = lib().pnbx_oracle_tree_eval(self._h, _p(targets), m, float(theta), want, _p(pot), _p(acc), _p(cnt, _i64))
+        rc = lib().pnbx_oracle_tree_eval_range(self._h, _p(targets), int(begin), m, float(theta), want, _p(pot), _p(acc),
+                                               _p(cnt, _i64))
         if rc:
             raise ValueError(lib().pnbx_oracle_last_error().decode())
         if counters:

@@ -9,9 +9,18 @@ the GIL for the duration of every call, like ``py.allow_threads`` in gravity.rs:
 There is no CPU fallback: if the library or a CUDA device is missing the calls raise.
 ``threads`` is accepted for signature compatibility and ignored (it sized the rayon pool).
 
-Additive, keyword-only extensions (not in the reference): ``precision=`` ("f32" | "f64") and
-``device=`` on every call, ``Octree.eval``/``tree_eval_device`` style helpers live in
-``pynbodyext.gravity.device``.
+Additive, keyword-only extensions (not in the reference): ``precision=`` and ``device=`` on every call; the
+device-resident variants live in ``pynbodyext.gravity.device``.
+
+Precision. The reference is float64 throughout; BASELINE's north_star asks for fp32 interaction arithmetic
+(accumulated in float64, RMS error ~1e-7 at the tested softenings). ``precision`` selects it per call:
+``"f32"``, ``"f64"`` (every pair in float64: the validation mode), or ``None`` / ``"auto"`` = the value of
+``$PNBX_PRECISION`` if set, else fp32 — except for UNSOFTENED direct sums of at most 2^30 pairs (the reference's
+documented small-N validation use of method="direct"), which run in float64: without a softening length a close pair's
+separation can be below the fp32 resolution of box-centred coordinates (6e-8 of the box).
+
+Devices. ``device=None`` is the current CUDA device; with ``$PNBX_DEVICES=all`` (or "0,1,...") host-array calls
+without an explicit device are spread over those GPUs (csrc/multi.cu), results identical.
 """
 from __future__ import annotations
 
@@ -94,6 +103,11 @@ def _load():
                                        C.POINTER(pnbx_opts)]
         L.pnbx_tree_build_mass.argtypes = [_vp, _vp]
         L.pnbx_tree_set_softenings.argtypes = [_vp, _vp]
+        L.pnbx_tree_get_order.argtypes = [_vp, C.c_int64, C.c_int64, _vp, C.POINTER(pnbx_opts)]
+        if hasattr(L, "pnbx_tree_build_mass_ex"):  # ABI additions of this round (older builds are used for A/B timing)
+            L.pnbx_tree_build_mass_ex.argtypes = [_vp, _vp, C.POINTER(pnbx_opts)]
+            L.pnbx_tree_set_softenings_ex.argtypes = [_vp, _vp, C.POINTER(pnbx_opts)]
+            L.pnbx_trim_memory.restype = None
         L.pnbx_tree_set_kernel.argtypes = [_vp, C.c_int]
         L.pnbx_tree_eval.argtypes = [_vp, _vp, C.c_int64, C.c_int64, C.c_double, C.c_int, _vp, _vp,
                                      C.POINTER(pnbx_opts)]
@@ -132,16 +146,30 @@ def _check(rc: int) -> None:
     raise RuntimeError(msg)
 
 
-def _opts(device=None, precision=None, mem_space=MEM_HOST, stream=None):
+AUTO_F64_MAX_PAIRS = 1 << 30
+
+
+def resolve_precision(precision, unsoftened_pairs=None):
+    """'f32' | 'f64' for a call (module docstring). unsoftened_pairs: N*M of a direct sum without softening."""
+    if precision in (None, "auto"):
+        env = os.environ.get("PNBX_PRECISION", "").strip().lower()
+        if env in ("f32", "f64"):
+            return env
+        if env not in ("", "auto"):
+            raise ValueError("PNBX_PRECISION must be 'f32', 'f64' or 'auto'")
+        return "f64" if (unsoftened_pairs is not None and unsoftened_pairs <= AUTO_F64_MAX_PAIRS) else "f32"
+    if precision in ("f32", PREC_F32):
+        return "f32"
+    if precision in ("f64", PREC_F64):
+        return "f64"
+    raise ValueError("precision must be 'f32', 'f64' or 'auto'")
+
+
+def _opts(device=None, precision=None, mem_space=MEM_HOST, stream=None, unsoftened_pairs=None):
     o = pnbx_opts()
     o.device = -1 if device is None else int(device)
     o.mem_space = mem_space
-    if precision in (None, "f32", PREC_F32):
-        o.precision = PREC_F32
-    elif precision in ("f64", PREC_F64):
-        o.precision = PREC_F64
-    else:
-        raise ValueError("precision must be 'f32' or 'f64'")
+    o.precision = PREC_F64 if resolve_precision(precision, unsoftened_pairs) == "f64" else PREC_F32
     o.flags = 0
     o.stream = stream
     o.shard_rank, o.shard_world, o.shard_block = 0, 1, 0
@@ -198,7 +226,7 @@ def _direct(positions, targets, masses, softenings, kernel, want, device, precis
     m = n if tgt is None else tgt.shape[0]
     pot = np.empty(m, dtype=np.float64) if want & WANT_POT else None
     acc = np.empty((m, 3), dtype=np.float64) if want & WANT_ACC else None
-    o = _opts(device, precision)
+    o = _opts(device, precision, unsoftened_pairs=n * m if k == -1 else None)
     rc = _load().pnbx_direct(_ptr(pos), _ptr(m_arr), _ptr(h_arr), n, _ptr(tgt), m, 0, k, want, _ptr(pot), _ptr(acc),
                              C.byref(o))
     _check(rc)
@@ -291,17 +319,17 @@ class Octree:
                                       C.byref(o)))
         return pot, acc
 
-    def compute_accelerations(self, theta, threads=0):
-        return self._eval(None, theta, WANT_ACC, method="compute_accelerations")[1]
+    def compute_accelerations(self, theta, threads=0, *, precision=None):
+        return self._eval(None, theta, WANT_ACC, method="compute_accelerations", precision=precision)[1]
 
-    def compute_potentials(self, theta, threads=0):
-        return self._eval(None, theta, WANT_POT, method="compute_potentials")[0]
+    def compute_potentials(self, theta, threads=0, *, precision=None):
+        return self._eval(None, theta, WANT_POT, method="compute_potentials", precision=precision)[0]
 
-    def accelerations_at_points(self, points, theta, threads=0):
-        return self._eval(points, theta, WANT_ACC, method="accelerations_at_points")[1]
+    def accelerations_at_points(self, points, theta, threads=0, *, precision=None):
+        return self._eval(points, theta, WANT_ACC, method="accelerations_at_points", precision=precision)[1]
 
-    def potentials_at_points(self, points, theta, threads=0):
-        return self._eval(points, theta, WANT_POT, method="potentials_at_points")[0]
+    def potentials_at_points(self, points, theta, threads=0, *, precision=None):
+        return self._eval(points, theta, WANT_POT, method="potentials_at_points", precision=precision)[0]
 
     def walk_counters(self, theta, points=None, tgt_begin=0, count=None) -> dict:
         """Totals over the targets of node visits / accepts / leaf visits / leaf particles of the walk

@@ -12,6 +12,9 @@ Behaviour kept from the reference, including its quirks:
 
 One deliberate difference: inputs that are already float64 C-contiguous are not copied in
 ``__init__`` (the reference ``astype`` copies, base.py:199-200); the device upload is the copy.
+
+Additive keyword (not in the reference): ``precision=`` on ``Gravity(...)`` and on every method
+(``"f32"`` | ``"f64"`` | ``None`` = auto, see ``pynbodyext._rust``).
 """
 from __future__ import annotations
 
@@ -56,7 +59,7 @@ class TreeOptions:
     kernel: KernelKind = KernelKind.No
 
 
-def _build_tree(positions, masses, softening, options: TreeOptions):
+def _build_tree(positions, masses, softening, options: TreeOptions, precision=None):
     return _Octree(
         positions,
         masses,
@@ -64,6 +67,7 @@ def _build_tree(positions, masses, softening, options: TreeOptions):
         options.multipole_order,
         softening,
         options.kernel.value,
+        precision=precision,
     )
 
 
@@ -81,7 +85,8 @@ class Gravity:
     ``multipole_order``.
     """
 
-    def __init__(self, positions, masses, softening=None, kernel=KernelKind.No, leaf_capacity=8, multipole_order=3):
+    def __init__(self, positions, masses, softening=None, kernel=KernelKind.No, leaf_capacity=8, multipole_order=3, *,
+                 precision=None):
         pos, mass = map(np.asarray, (positions, masses))
         if pos.ndim != 2 or pos.shape[1] != 3:
             raise ValueError("positions must be a float64 array of shape (N, 3)")
@@ -100,6 +105,7 @@ class Gravity:
         self.mass = np.ascontiguousarray(mass, dtype=np.float64)
         self.softening = soft_arr
         self.tree_options = TreeOptions(leaf_capacity, multipole_order, kernel=KernelKind(kernel))
+        self.precision = precision
         self._tree = None  # built lazily
 
     # ------------------------------------------------------------------ tree cache
@@ -109,39 +115,50 @@ class Gravity:
         if options == self.tree_options:
             return self.tree
         logger.debug("Building new Octree with leaf_capacity=%d, multipole_order=%d", leaf_capacity, multipole_order)
-        return _build_tree(self.pos, self.mass, self.softening, options)
+        return _build_tree(self.pos, self.mass, self.softening, options, self.precision)
 
     @property
     def tree(self):
         if self._tree is None:
-            self._tree = _build_tree(self.pos, self.mass, self.softening, self.tree_options)
+            self._tree = _build_tree(self.pos, self.mass, self.softening, self.tree_options, self.precision)
         return self._tree
+
+    def _prec(self, precision):
+        return self.precision if precision is None else precision
 
     def _kernel(self, kernel):
         return self.tree_options.kernel if kernel is None else KernelKind(kernel)
 
     # ------------------------------------------------------------------ direct summation
-    def direct_potentials(self, positions=None, threads=0, kernel=None):
+    def direct_potentials(self, positions=None, threads=0, kernel=None, *, precision=None):
         k = self._kernel(kernel)
+        p = self._prec(precision)
         if positions is None:
-            return _direct_potentials_py(self.pos, self.mass, threads, self.softening, k.value)
-        return _direct_potentials_at_points_py(self.pos, _targets(positions), self.mass, threads, self.softening, k.value)
+            return _direct_potentials_py(self.pos, self.mass, threads, self.softening, k.value, precision=p)
+        return _direct_potentials_at_points_py(self.pos, _targets(positions), self.mass, threads, self.softening, k.value,
+                                               precision=p)
 
-    def direct_accelerations(self, positions=None, threads=0, kernel=None):
+    def direct_accelerations(self, positions=None, threads=0, kernel=None, *, precision=None):
         k = self._kernel(kernel)
+        p = self._prec(precision)
         if positions is None:
-            return _direct_accelerations_py(self.pos, self.mass, threads, self.softening, k.value)
-        return _direct_accelerations_at_points_py(self.pos, _targets(positions), self.mass, threads, self.softening, k.value)
+            return _direct_accelerations_py(self.pos, self.mass, threads, self.softening, k.value, precision=p)
+        return _direct_accelerations_at_points_py(self.pos, _targets(positions), self.mass, threads, self.softening,
+                                                  k.value, precision=p)
 
     # ------------------------------------------------------------------ tree
-    def tree_potentials(self, positions=None, theta=0.7, threads=0, leaf_capacity=8, multipole_order=3, kernel=None):
+    def tree_potentials(self, positions=None, theta=0.7, threads=0, leaf_capacity=8, multipole_order=3, kernel=None, *,
+                        precision=None):
         tree = self.get_tree(leaf_capacity=leaf_capacity, multipole_order=multipole_order, kernel=self._kernel(kernel))
+        p = self._prec(precision)
         if positions is None:
-            return tree.compute_potentials(theta, threads)
-        return tree.potentials_at_points(_targets(positions), theta, threads)
+            return tree.compute_potentials(theta, threads, precision=p)
+        return tree.potentials_at_points(_targets(positions), theta, threads, precision=p)
 
-    def tree_accelerations(self, positions=None, theta=0.7, threads=0, leaf_capacity=8, multipole_order=3, kernel=None):
+    def tree_accelerations(self, positions=None, theta=0.7, threads=0, leaf_capacity=8, multipole_order=3, kernel=None, *,
+                           precision=None):
         tree = self.get_tree(leaf_capacity=leaf_capacity, multipole_order=multipole_order, kernel=self._kernel(kernel))
+        p = self._prec(precision)
         if positions is None:
-            return tree.compute_accelerations(theta, threads)
-        return tree.accelerations_at_points(_targets(positions), theta, threads)
+            return tree.compute_accelerations(theta, threads, precision=p)
+        return tree.accelerations_at_points(_targets(positions), theta, threads, precision=p)

@@ -92,6 +92,24 @@ class OctreeDevice:
             lib.pnbx_tree_destroy(h)
             self._h = None
 
+    # -- setters on device tensors (gravity.rs:228-265): stream-ordered on the caller's current stream
+    def build_mass(self, mass=None):
+        torch = _torch()
+        o = _b._opts(self._dev.index, None, mem_space=_b.MEM_DEVICE, stream=torch.cuda.current_stream(self._dev).cuda_stream)
+        if mass is not None and mass.shape != (self._n,):
+            raise ValueError("masses must be length N")
+        _b._check(_b._load().pnbx_tree_build_mass_ex(self._h, _dptr(mass), C.byref(o)))
+
+    def set_softenings(self, h=None):
+        torch = _torch()
+        o = _b._opts(self._dev.index, None, mem_space=_b.MEM_DEVICE, stream=torch.cuda.current_stream(self._dev).cuda_stream)
+        if h is not None and h.shape != (self._n,):
+            raise ValueError("softenings must be length N")
+        _b._check(_b._load().pnbx_tree_set_softenings_ex(self._h, _dptr(h), C.byref(o)))
+
+    def set_kernel(self, kernel=None):
+        _b._check(_b._load().pnbx_tree_set_kernel(self._h, _b._kernel_code(kernel, 0)))
+
     def info(self):
         inf = _b.pnbx_tree_info()
         _b._check(_b._load().pnbx_tree_get_info(self._h, C.byref(inf)))
@@ -114,12 +132,11 @@ class OctreeDevice:
         m = ms if ms is not None else (self._n - begin if count is None else int(count))
         out = torch.empty(m, dtype=torch.int64, device=self._dev)
         L = _b._load()
-        L.pnbx_tree_get_order.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(_b.pnbx_opts)]
         _b._check(L.pnbx_tree_get_order(self._h, int(begin), m, out.data_ptr(), C.byref(o)))
         return out
 
     def eval(self, theta, want=_b.WANT_POT, targets=None, tgt_begin=0, count=None, kernel_events=False,
-             tree_order=False, shard=None):
+             tree_order=False, shard=None, precision=None):
         """(pot | None, acc | None) for own particles [tgt_begin, tgt_begin+count) or for `targets` (M,3).
         tree_order=True: the range selects tree-order positions and results come back in that order
         (use .order(tgt_begin, count) to scatter them) — coherent warps, the right sharding for multi-GPU.
@@ -134,7 +151,7 @@ class OctreeDevice:
             ref = targets
         pot = torch.empty(m, dtype=torch.float64, device=self._dev) if want & _b.WANT_POT else None
         acc = torch.empty((m, 3), dtype=torch.float64, device=self._dev) if want & _b.WANT_ACC else None
-        o = _dev_opts(ref, self._precision, kernel_events)
+        o = _dev_opts(ref, self._precision if precision is None else precision, kernel_events)
         if tree_order:
             o.flags |= FLAG_TREE_ORDER
         self._shard(o, shard)
@@ -162,6 +179,11 @@ def last_kernel_ms() -> float:
     L.pnbx_last_kernel_ms.argtypes = [C.POINTER(C.c_double)]
     _b._check(L.pnbx_last_kernel_ms(C.byref(ms)))
     return ms.value
+
+
+def trim_memory() -> None:
+    """Return the library's cached device memory blocks that are not in use (pnbx_trim_memory)."""
+    _b._load().pnbx_trim_memory()
 
 
 def launch_count() -> int:

@@ -47,6 +47,7 @@ def _run(sim, positions, softening, method, threads, kernel, kwargs, want_acc):
         kernel=kernel,
         leaf_capacity=kwargs.get("leaf_capacity", 8),
         multipole_order=kwargs.get("multipole_order", 3),
+        precision=kwargs.get("precision"),  # additive: "f32" | "f64" | None (auto), see pynbodyext._rust
     )
     if isinstance(positions, SimArray):
         positions = positions.in_units(sim["pos"].units)

@@ -66,8 +66,13 @@ def test_python_api_surface():
     from pynbodyext.gravity import Gravity, KernelKind, calculate_acceleration, calculate_potential
     assert [k.name for k in KernelKind] == ["No", "Plummer", "Spline"] and KernelKind.Spline.value == 1
     sig = inspect.signature(Gravity.tree_potentials)
-    assert list(sig.parameters) == ["self", "positions", "theta", "threads", "leaf_capacity", "multipole_order", "kernel"]
+    # the reference's positional parameters, in order; additive extensions are keyword-only
+    assert list(sig.parameters)[:7] == ["self", "positions", "theta", "threads", "leaf_capacity", "multipole_order", "kernel"]
+    assert all(p.kind is inspect.Parameter.KEYWORD_ONLY for p in list(sig.parameters.values())[7:])
     assert sig.parameters["theta"].default == 0.7 and sig.parameters["multipole_order"].default == 3
+    sig = inspect.signature(Gravity.__init__)
+    assert list(sig.parameters)[:7] == ["self", "positions", "masses", "softening", "kernel", "leaf_capacity", "multipole_order"]
+    assert all(p.kind is inspect.Parameter.KEYWORD_ONLY for p in list(sig.parameters.values())[7:])
     sig = inspect.signature(calculate_potential)
     assert list(sig.parameters)[:5] == ["sim", "positions", "softening", "method", "threads"]
     assert sig.parameters["method"].default == "tree"

@@ -2,12 +2,16 @@
 oracle / float64 subsamples (the oracle cannot run the full sizes in test time).
 
 config 2: Hernquist N = 1e6, Plummer eps = 0.01, direct sum fp32 vs float64 reference on a target subsample
-config 3: NFW + disc N = 1e7, spline per-particle softening, tree theta 0.5 / 0.7, order 3, leaf 8
+config 3: NFW + disc N = 1e7, spline per-particle softening, tree theta 0.5 / 0.7, order 3, leaf 8 — against the
+          oracle's tree built from the same 1e7 particles (bit-exact tree, equal walks on a 2e4-target subsample)
+config 4/5 shape: dm/gas/star zoom set at N = 1e7 (the oracle cannot hold 1e8): oracle tree, self + (R,z) grid
+          targets, float64 direct sum as truth for the grid potentials. The N = 1e8 runs themselves are measured and
+          spot-checked by bench.py --gpus 8 (tree_1e8 section).
 """
 import numpy as np
 import pytest
 
-from benchmarks.synthetic import hernquist, nfw_disc
+from benchmarks.synthetic import hernquist, nfw_disc, rz_grid_targets, zoom_range, zoom_set
 
 pytestmark = pytest.mark.gpu
 
@@ -65,11 +69,110 @@ def test_config2_target_shards_reassemble(config2):
     assert float(rel.max()) < 1e-5 and float(rel.pow(2).mean().sqrt()) < 1e-6
 
 
+def flat_leaves(topo):
+    """Particle lists of all leaves, concatenated in ascending node id (vectorised leaf_sets for 1e7-size trees)."""
+    ids = np.nonzero(topo["leaf_count"] >= 0)[0]
+    start, cnt = topo["leaf_start"][ids], topo["leaf_count"][ids]
+    off = np.concatenate([[0], np.cumsum(cnt)])
+    k = np.arange(off[-1]) - np.repeat(off[:-1], cnt) + np.repeat(start, cnt)
+    return ids, cnt, topo["leaf_particles"][k]
+
+
+def assert_same_tree_as_oracle(g, o):
+    """Topology (reference numbering, links, geometry, path keys, leaf particle lists) and payloads: bit-exact."""
+    ig, io = g.info(), o.info()
+    assert ig["n_nodes"] == io["n_nodes"] and ig["n_leaves"] == io["n_leaves"] and ig["depth"] == io["depth"]
+    tg, to = g.topology(), o.topology()
+    for k in ("center", "half", "depth", "first_subnode", "next_branch", "leaf_count", "path_hi", "path_lo"):
+        assert np.array_equal(tg[k], to[k]), k
+    for x, y in zip(flat_leaves(tg), flat_leaves(to)):
+        assert np.array_equal(x, y)
+    del tg, to
+    pg, po = g.payload(), o.payload()
+    for k in ("mass", "com", "hmax", "moments"):
+        assert np.array_equal(pg[k], po[k]), k
+
+
+def check_against_oracle_subsample(tree, otree, theta, lo, cnt, grid):
+    """GPU fp32 / f64 walk vs the ORACLE's walk on a target subsample: identical interaction lists (counters equal),
+    results within 1e-5 (fp32, north_star) / 1e-11 (f64). Self targets [lo, lo+cnt) and at-points grid targets."""
+    p_o, a_o, c_o = otree.eval(theta, begin=lo, count=cnt, counters=True)
+    c_g = tree.walk_counters(theta, tgt_begin=lo, count=cnt)
+    # the oracle counts both of its passes (potential + acceleration); the traversal is the same in both
+    assert {k: 2 * c_g[k] for k in c_o} == c_o
+    p32, a32 = tree._eval(None, theta, 3, tgt_begin=lo, count=cnt)
+    p64, a64 = tree._eval(None, theta, 3, tgt_begin=lo, count=cnt, precision="f64")
+    assert rms_rel(p32, p_o) < 1e-5 and rms_rel_vec(a32, a_o) < 1e-5
+    assert rms_rel(p64, p_o) < 1e-11 and rms_rel_vec(a64, a_o) < 1e-11
+    pq_o, aq_o, cq_o = otree.eval(theta, targets=grid, counters=True)
+    cq_g = tree.walk_counters(theta, points=grid)
+    assert {k: 2 * cq_g[k] for k in cq_o} == cq_o
+    pq32, aq32 = tree._eval(grid, theta, 3)
+    pq64, aq64 = tree._eval(grid, theta, 3, precision="f64")
+    assert rms_rel(pq32, pq_o) < 1e-5 and rms_rel_vec(aq32, aq_o) < 1e-5
+    assert rms_rel(pq64, pq_o) < 1e-11 and rms_rel_vec(aq64, aq_o) < 1e-11
+    return p64, a64, pq64, aq64
+
+
 @pytest.fixture(scope="module")
 def config3():
     import pynbodyext._rust as r
     pos, m, h = nfw_disc(10_000_000, seed=3)
     return pos, m, h, r.Octree(pos, m, 8, 3, h, 1)
+
+
+def test_config3_matches_oracle_tree_at_full_size(config3):
+    # BASELINE config 3 at its full size against the ORACLE (serial reference build, ~15 s at 1e7): bit-exact tree,
+    # equal interaction lists and results on 2e4 self targets + 2e4 grid points, theta 0.5 and 0.7
+    from oracle import oracle as O
+    pos, m, h, tree = config3
+    ot = O.Tree(pos, m, 8, 3, h, 1)
+    assert_same_tree_as_oracle(tree, ot)
+    grid = rz_grid_targets(20_000, seed=5, rmax=1.0)
+    for theta in (0.5, 0.7):
+        check_against_oracle_subsample(tree, ot, theta, 4_000_000, 20_000, grid)
+
+
+@pytest.fixture(scope="module")
+def config4():
+    import pynbodyext._rust as r
+    pos, m, h = zoom_set(10_000_000, seed=4)
+    return pos, m, h, r.Octree(pos, m, 8, 3, h, 1)
+
+
+def test_config4_zoom_matches_oracle_tree(config4):
+    # BASELINE configs 4 / 5 shape (dm/gas/star zoom set, spline softening, gas h ∝ spacing, theta 0.7, order 3) at
+    # N = 1e7: depth >= 18 and a softened core where the hmax gate opens whole subtrees (tree.rs:55-71) — the regime
+    # of the N = 1e8 runs. Bit-exact tree, equal interaction lists, results vs the oracle on self and grid targets.
+    from oracle import oracle as O
+    pos, m, h, tree = config4
+    ot = O.Tree(pos, m, 8, 3, h, 1)
+    assert tree.info()["depth"] >= 18
+    assert_same_tree_as_oracle(tree, ot)
+    grid = rz_grid_targets(20_000, seed=5)
+    p64, a64, pq64, aq64 = check_against_oracle_subsample(tree, ot, 0.7, 5_000_000, 20_000, grid)
+    # config 5's truth: float64 DIRECT sum at the grid points (at-points: h = max(h_j, 0), no self term) — the tree's
+    # truncation error at theta 0.7 / order 3 is far below 1e-2 (single_node.rs bound); measured median ~1e-4
+    import pynbodyext._rust as r
+    sub = grid[::10]
+    p_d = r.direct_potentials_at_points_py(pos, np.ascontiguousarray(sub), m, 0, h, 1, precision="f64")
+    a_d = r.direct_accelerations_at_points_py(pos, np.ascontiguousarray(sub), m, 0, h, 1, precision="f64")
+    ep = np.abs(pq64[::10] - p_d) / np.abs(p_d)
+    ea = np.linalg.norm(aq64[::10] - a_d, axis=1) / np.linalg.norm(a_d, axis=1)
+    assert np.median(ep) < 2e-4 and ep.max() < 1e-2
+    assert np.median(ea) < 2e-3 and np.percentile(ea, 90) < 1e-2
+
+
+def test_zoom_set_is_independent_of_the_rank_layout():
+    # the N = 1e8 benchmark generates each rank's shard separately: any split reproduces the same global set
+    n = 3_000_000
+    pos, m, h = zoom_set(n, seed=4)
+    for world in (2, 8):
+        b = [(n * r) // world for r in range(world + 1)]
+        parts = [zoom_range(n, lo, hi, seed=4) for lo, hi in zip(b[:-1], b[1:])]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), pos)
+        assert np.array_equal(np.concatenate([p[1] for p in parts]), m)
+        assert np.array_equal(np.concatenate([p[2] for p in parts]), h)
 
 
 def test_config3_tree_structure_and_payload_invariants(config3):
