@@ -12,6 +12,7 @@
 // The source range is split over blockIdx.y so the grid holds >= ~20 waves of work items; split
 // partials are combined in a fixed order (deterministic, no float atomics).
 #include <cfloat>
+#include <mutex>
 
 #include "common.cuh"
 #include "spline.cuh"
@@ -49,6 +50,13 @@ struct DirectPlan {
     float eps2_f, mass_f;
     double eps2_d, mass_d;
 };
+
+// The plan is read by the kernels from CONSTANT memory: a stream-ordered device-to-device copy puts it into one of
+// PLAN_SLOTS slots of c_plans (slot index = kernel parameter), so eps^2 and the gate arrive through the constant bank in
+// uniform registers exactly like kernel parameters would (as a value loaded from global memory eps^2 occupied a vector
+// register and made every FFMA2 of the r^2 chain a three-vector-operand instruction: measured 2 % slower).
+constexpr int PLAN_SLOTS = 64;
+__constant__ DirectPlan c_plans[PLAN_SLOTS];
 
 template <class T>
 struct alignas(sizeof(T) * 4) Vec4 {
@@ -224,11 +232,12 @@ template <int WANT, int SOFT, class T, int TILE>
 __global__ void __launch_bounds__(DT, PNBX_MINB)
 direct_kernel(const Vec4<T>* __restrict__ src, const T* __restrict__ src_h, int64_t n_src,
               const Vec4<T>* __restrict__ tgt, const T* __restrict__ tgt_h, int64_t m, int64_t self_base,
-              const DirectPlan* __restrict__ plan, int my_variant, int tiles_per_split, double* __restrict__ out_pot,
+              int plan_slot, int my_variant, int tiles_per_split, double* __restrict__ out_pot,
               double* __restrict__ out_acc) {
     constexpr bool PAIR_H = (SOFT == SOFT_PLUMMER_PAIR || SOFT == SOFT_SPLINE);
-    if (plan->variant != my_variant) return;  // not the variant this call's data needs (whole grid, before any barrier)
-    const T eps2_const = sizeof(T) == 4 ? (T)plan->eps2_f : (T)plan->eps2_d;
+    const DirectPlan& plan = c_plans[plan_slot];
+    if (plan.variant != my_variant) return;  // not the variant this call's data needs (whole grid, before any barrier)
+    const T eps2_const = sizeof(T) == 4 ? (T)plan.eps2_f : (T)plan.eps2_d;
     __shared__ Vec4<T> s_src[STAGES][TILE];
     __shared__ alignas(16) T s_h[PAIR_H ? STAGES : 1][PAIR_H ? TILE : 4];
     __shared__ alignas(8) uint64_t s_full[STAGES];
@@ -395,11 +404,12 @@ constexpr int TILEP = TILE32 / 2;  // pair records per stage
 template <int WANT, bool CONSTM>
 __global__ void __launch_bounds__(DT, PNBX_MINB)
 direct_kernel_f2(const Pair8* __restrict__ src, int64_t n_src, const Vec4<float>* __restrict__ tgt, int64_t m,
-                 int64_t self_base, const DirectPlan* __restrict__ plan, int tiles_per_split,
+                 int64_t self_base, int plan_slot, int tiles_per_split,
                  double* __restrict__ out_pot, double* __restrict__ out_acc) {
     __shared__ Pair8 s_src[STAGES][TILEP];
-    if (plan->variant != (CONSTM ? V_F2_CONSTM : V_F2)) return;
-    const float eps2_const = plan->eps2_f;
+    const DirectPlan& plan = c_plans[plan_slot];
+    if (plan.variant != (CONSTM ? V_F2_CONSTM : V_F2)) return;
+    const float eps2_const = plan.eps2_f;
     __shared__ alignas(8) uint64_t s_full[STAGES];
     const int tid = threadIdx.x;
     const int64_t n_pairs = (n_src + 1) / 2;  // the odd tail is padded by pack_pairs (zero mass, far away)
@@ -518,7 +528,7 @@ direct_kernel_f2(const Pair8* __restrict__ src, int64_t n_src, const Vec4<float>
         __syncthreads();
     }
     const int64_t split_off = (int64_t)blockIdx.y * m;
-    const double ms = CONSTM ? plan->mass_d : 1.0;
+    const double ms = CONSTM ? plan.mass_d : 1.0;
 #pragma unroll
     for (int k = 0; k < TPT; ++k) {
         int64_t i = tgt_base + k * DT + tid;
@@ -580,10 +590,10 @@ template <int WANT, int HMODE>
 __global__ void __launch_bounds__(DT, PNBX_MINB)
 direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h2, int64_t n_src,
                   const Vec4<float>* __restrict__ tgt, const float* __restrict__ tgt_h2, int64_t m, int64_t self_base,
-                  const DirectPlan* __restrict__ plan, int tiles_per_split, double* __restrict__ out_pot,
+                  int plan_slot, int tiles_per_split, double* __restrict__ out_pot,
                   double* __restrict__ out_acc) {
     __shared__ Pair8 s_src[STAGES][TILEP];
-    if (plan->variant != V_F2H) return;
+    if (c_plans[plan_slot].variant != V_F2H) return;
     __shared__ alignas(16) float2 s_h2[STAGES][TILEP];
     __shared__ alignas(8) uint64_t s_full[STAGES];
     const int tid = threadIdx.x;
@@ -594,7 +604,7 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
     const int64_t tgt_base = (int64_t)blockIdx.x * (DT * TPT);
 
     f2_t xi[TPT], yi[TPT], zi[TPT];
-    float th2[TPT];
+    float th2[TPT], th2f[TPT];
 #pragma unroll
     for (int k = 0; k < TPT; ++k) {
         int64_t i = tgt_base + k * DT + tid;
@@ -602,6 +612,7 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
         Vec4<float> t = tgt[i];
         xi[k] = f2_pack(t.x, t.x); yi[k] = f2_pack(t.y, t.y); zi[k] = f2_pack(t.z, t.z);
         th2[k] = tgt_h2 ? tgt_h2[i] : 0.f;
+        th2f[k] = HMODE == 1 ? fmaxf(th2[k], FLT_MIN) : th2[k];
     }
     // global source index of this thread's k-th target: g0 + k*DT (lanes past the end are clamped duplicates whose
     // results are never stored, so their index does not matter)
@@ -647,16 +658,22 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
             f2_t ax[TPT], ay[TPT], az[TPT], p[TPT];
 #pragma unroll
             for (int k = 0; k < TPT; ++k) ax[k] = ay[k] = az[k] = p[k] = 0ull;  // {+0.f, +0.f}
-            bool inside = false;
+            // spline: bit g of `inside` = some pair of records [8g, 8g+8) lies inside its softening radius for one of
+            // this lane's targets; pass 2 revisits only those groups (TILEP / 8 = 32 groups: one 32-bit mask per lane)
+            unsigned inside = 0u;
+            static_assert(TILEP == 256, "the group mask of the spline pass assumes 32 groups of 8 pair records");
 #pragma unroll UNROLL_F2
             for (int q = 0; q < TILEP; ++q) {
                 const ulonglong4 v = *reinterpret_cast<const ulonglong4*>(&s_src[st][q]);  // {x0x1, y0y1, z0z1, m0m1}
                 const float2 hh = s_h2[st][q];
+                const unsigned gbit = 1u << (q >> 3);
 #pragma unroll
                 for (int k = 0; k < TPT; ++k) {
                     const f2_t dx = f2_sub(v.x, xi[k]), dy = f2_sub(v.y, yi[k]), dz = f2_sub(v.z, zi[k]);
-                    const float h2a = fmaxf(hh.x, th2[k]), h2b = fmaxf(hh.y, th2[k]);
-                    f2_t r2 = f2_fma(dx, dx, HMODE == 1 ? f2_pack(fmaxf(h2a, FLT_MIN), fmaxf(h2b, FLT_MIN)) : tiny2);
+                    // th2f[k] = max(th2[k], FLT_MIN) for Plummer (the + R2_TINY folded into the softening), th2[k] for
+                    // the spline: one max per source, h^2 = max(h_s^2, h_t^2)
+                    const float h2a = fmaxf(hh.x, th2f[k]), h2b = fmaxf(hh.y, th2f[k]);
+                    f2_t r2 = f2_fma(dx, dx, HMODE == 1 ? f2_pack(h2a, h2b) : tiny2);
                     r2 = f2_fma(dy, dy, r2);
                     r2 = f2_fma(dz, dz, r2);
                     float ra, rb;
@@ -666,7 +683,7 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
                         float m0, m1;
                         f2_unpack(v.w, m0, m1);
                         const bool ia = ra < h2a, ib = rb < h2b;  // r < h: left to pass 2 (no add-then-subtract)
-                        inside |= ia | ib;
+                        inside |= (ia | ib) ? gbit : 0u;
                         mm = f2_pack(ia ? 0.f : m0, ib ? 0.f : m1);
                     }
                     const f2_t rinv = f2_pack(rsqrt_fast(ra), rsqrt_fast(rb));
@@ -691,9 +708,14 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
                 }
                 if (WANT & PNBX_WANT_POT) { f2_unpack(p[k], a, b); sp[k] = -(a + b); }
             }
-            if (HMODE == 2 && __any_sync(0xffffffffu, inside)) {
-                if (inside) {
-                    for (int q = 0; q < TILEP; ++q) {
+            if (HMODE == 2) {
+                // pass 2: W2 terms of the pairs with r < h, only in the flagged groups of 8 pair records (each lane walks
+                // its own set bits; the predicate inside pair_h2_scalar is pass 1's, bit for bit)
+                while (inside) {
+                    const int g = __ffs((int)inside) - 1;
+                    inside &= inside - 1u;
+#pragma unroll 2
+                    for (int q = 8 * g; q < 8 * g + 8; ++q) {
                         const Pair8 pr = s_src[st][q];
                         const float2 hh = s_h2[st][q];
 #pragma unroll
@@ -879,7 +901,7 @@ __global__ void classify_direct(ClassifyArgs c, DirectPlan* __restrict__ plan) {
 
 template <int WANT, int SOFT, class T, int TILE>
 void launch_direct_t(const Vec4<T>* src, const T* src_h, int64_t n, const Vec4<T>* tgt, const T* tgt_h, int64_t m,
-                     int64_t self_base, const DirectPlan* plan, int variant, int splits, int tiles_per_split, double* pot,
+                     int64_t self_base, int plan, int variant, int splits, int tiles_per_split, double* pot,
                      double* acc, cudaStream_t s) {
     dim3 grid((unsigned)ceil_div(m, DT * TPT), (unsigned)splits);
     PNBX_LAUNCH((direct_kernel<WANT, SOFT, T, TILE>), grid, DT, 0, s, src, src_h, n, tgt, tgt_h, m, self_base, plan, variant,
@@ -888,7 +910,7 @@ void launch_direct_t(const Vec4<T>* src, const T* src_h, int64_t n, const Vec4<T
 
 template <class T, int TILE>
 void launch_direct(int want, int soft, const Vec4<T>* src, const T* src_h, int64_t n, const Vec4<T>* tgt,
-                   const T* tgt_h, int64_t m, int64_t self_base, const DirectPlan* plan, int variant, int splits,
+                   const T* tgt_h, int64_t m, int64_t self_base, int plan, int variant, int splits,
                    int tiles_per_split, double* pot, double* acc, cudaStream_t s) {
 #define PNBX_CASE(W, S)                                                                                          \
     if (want == W && soft == S) {                                                                                \
@@ -901,6 +923,34 @@ void launch_direct(int want, int soft, const Vec4<T>* src, const T* src_h, int64
     PNBX_CASE(1, SOFT_SPLINE) PNBX_CASE(2, SOFT_SPLINE) PNBX_CASE(3, SOFT_SPLINE)
 #undef PNBX_CASE
     throw ArgError{PNBX_ERR_ARG, "internal: no direct kernel variant"};
+}
+
+// Constant-memory plan slots, per device: a slot is reused only after the kernels of its previous user have run
+// (event), so any number of calls may be queued on any streams.
+struct PlanSlots {
+    std::mutex mu;
+    unsigned next = 0;
+    cudaEvent_t done[PLAN_SLOTS] = {};
+};
+PlanSlots g_plan_slots[KernelEvents::MAXDEV];
+
+int acquire_plan_slot(int device, cudaStream_t s, const DirectPlan* d_plan) {
+    PlanSlots& ps = g_plan_slots[device < KernelEvents::MAXDEV ? device : 0];
+    int slot;
+    {
+        std::lock_guard<std::mutex> lock(ps.mu);
+        slot = (int)(ps.next++ % PLAN_SLOTS);
+        if (!ps.done[slot]) PNBX_CUDA(cudaEventCreateWithFlags(&ps.done[slot], cudaEventDisableTiming));
+        else PNBX_CUDA(cudaStreamWaitEvent(s, ps.done[slot], 0));
+    }
+    PNBX_CUDA(cudaMemcpyToSymbolAsync(c_plans, d_plan, sizeof(DirectPlan), (size_t)slot * sizeof(DirectPlan),
+                                      cudaMemcpyDeviceToDevice, s));
+    return slot;
+}
+void release_plan_slot(int device, cudaStream_t s, int slot) {
+    PlanSlots& ps = g_plan_slots[device < KernelEvents::MAXDEV ? device : 0];
+    std::lock_guard<std::mutex> lock(ps.mu);
+    PNBX_CUDA(cudaEventRecord(ps.done[slot], s));
 }
 
 template <class T, int TILE>
@@ -935,6 +985,7 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     ClassifyArgs ca{hpart.get(), mpart.get(), NPART, kernel, self ? 1 : 0, packed ? 1 : 0, allow_f2h ? 1 : 0,
                     allow_constm ? 1 : 0};
     PNBX_LAUNCH(classify_direct, 1, 1, 0, s, ca, plan.get());
+    const int slot = acquire_plan_slot(ex.device, s, plan.get());
     // which variants can the decision come out as? (everything the host can rule out is not even launched)
     const bool may_const = true;                                   // constant / absent softening
     const bool may_pair = have_h;                                  // per-pair softening
@@ -999,7 +1050,7 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     if constexpr (sizeof(T) == 4) {
         const Pair8* sp = srcp.get();
         const Vec4<float>* tp = reinterpret_cast<const Vec4<float>*>(tgt4.get());
-        const DirectPlan* pl = plan.get();
+        const int pl = slot;
 #define PNBX_F2(W)                                                                                                     \
     if (want == W) {                                                                                                   \
         if (may_f2_constm) PNBX_LAUNCH((direct_kernel_f2<W, true>), grid, DT, 0, s, sp, n, tp, m, sb, pl, tiles_per_split, kp, ka);  \
@@ -1016,12 +1067,13 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
 #undef PNBX_F2
     }
     if (may_scalar_const)
-        launch_direct<T, TILE>(want, SOFT_PLUMMER_CONST, src4.get(), nullptr, n, tgt4.get(), nullptr, m, sb, plan.get(),
+        launch_direct<T, TILE>(want, SOFT_PLUMMER_CONST, src4.get(), nullptr, n, tgt4.get(), nullptr, m, sb, slot,
                                V_SCALAR_CONST, (int)splits, tiles_per_split, kp, ka, s);
     if (may_scalar_pair)
         launch_direct<T, TILE>(want, kernel == PNBX_KERNEL_SPLINE ? SOFT_SPLINE : SOFT_PLUMMER_PAIR, src4.get(), srch.get(), n,
-                               tgt4.get(), self ? srch.get() + tgt_begin : nullptr, m, sb, plan.get(), V_SCALAR_PAIR,
+                               tgt4.get(), self ? srch.get() + tgt_begin : nullptr, m, sb, slot, V_SCALAR_PAIR,
                                (int)splits, tiles_per_split, kp, ka, s);
+    release_plan_slot(ex.device, s, slot);
     kernel_events().end(s);
     PNBX_CUDA(cudaGetLastError());
     if (splits > 1) {
