@@ -708,6 +708,7 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
                 }
                 if (WANT & PNBX_WANT_POT) { f2_unpack(p[k], a, b); sp[k] = -(a + b); }
             }
+#ifndef PNBX_EXPERIMENT_NO_PASS2
             if (HMODE == 2) {
                 // pass 2: W2 terms of the pairs with r < h, only in the flagged groups of 8 pair records (each lane walks
                 // its own set bits; the predicate inside pair_h2_scalar is pass 1's, bit for bit)
@@ -728,6 +729,7 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
                     }
                 }
             }
+#endif
 #pragma unroll
             for (int k = 0; k < TPT; ++k) {
                 if (WANT & PNBX_WANT_ACC) { Ax[k] += (double)sax[k]; Ay[k] += (double)say[k]; Az[k] += (double)saz[k]; }

@@ -25,7 +25,12 @@ struct alignas(64) NodeRec {
     int32_t first;        // internal: first_subnode; leaf: first particle (sorted order)
     int32_t kind;         // >= 0: leaf with `kind` particles; -1: internal; -2: zero mass (skip subtree)
     int32_t nleaf;        // leaf records only: number of reference leaves this record stands for (see below)
+    int32_t ref;          // the node's id in the reference numbering (the float64 payload arrays are indexed by it)
+    int32_t pad_;
 };
+// Walk records (and the fp32 moment records) are stored in DEPTH-FIRST order, not in the reference numbering: the walk
+// is a depth-first sweep with skips, so `first` is the next record in memory and every warp moves monotonically forward
+// through the array (the reference numbering keeps siblings together but scatters subtrees). Links are remapped.
 // Leaf runs. Every lane that opens a node visits ALL of its children, and leaves are always summed directly, so a
 // maximal run of consecutive non-zero-mass sibling leaves (consecutive reference ids, contiguous sorted particles) is
 // visited by the same lanes one leaf after the other. The walk records merge such a run into the record of its first
@@ -85,6 +90,7 @@ struct pnbx_tree_impl {
     // INTERNAL nodes grouped by level (reference ids, for the bottom-up payload sweeps): those of level d are
     // level_ids[ilevel_off[d] .. ilevel_off[d+1]); the leaves follow behind all internal nodes
     DevBuf<int32_t> level_ids;
+    DevBuf<int32_t> dfs_of_ref;        // depth-first index of every node (the order of the walk records)
     std::vector<int64_t> ilevel_off;
     int64_t n_internal = 0;
 

@@ -279,7 +279,8 @@ struct FinalArrays {
 // range (depth-first order), or "none" (-1) at the end of the particle list.
 __global__ void scatter_nodes(DfsNodes d, const int32_t* __restrict__ scan, const int32_t* __restrict__ ref,
                               const int32_t* __restrict__ base, int64_t nn, int64_t n, FinalArrays f,
-                              uint8_t* __restrict__ sortkey, int32_t* __restrict__ sortval) {
+                              uint8_t* __restrict__ sortkey, int32_t* __restrict__ sortval,
+                              int32_t* __restrict__ dfs_of_ref) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nn) return;
     const int32_t r = ref[i];
@@ -297,6 +298,7 @@ __global__ void scatter_nodes(DfsNodes d, const int32_t* __restrict__ scan, cons
     f.nchild[r] = (uint8_t)nc;
     sortkey[i] = nc > 0 ? d.level[i] : (uint8_t)64;  // internal nodes grouped by level, all leaves behind them
     sortval[i] = r;
+    dfs_of_ref[r] = (int32_t)i;
 }
 __global__ void empty_root(const double* __restrict__ root4, FinalArrays f) {
     f.center[0] = root4[0]; f.center[1] = root4[1]; f.center[2] = root4[2]; f.half[0] = root4[3];
@@ -491,7 +493,8 @@ __global__ void build_walk_records(const double* __restrict__ nmass, const doubl
                                    const double* __restrict__ half, const double* __restrict__ hmax, double csep,
                                    const uint8_t* __restrict__ nchild, const uint32_t* __restrict__ start,
                                    const uint32_t* __restrict__ count, const int32_t* __restrict__ first_subnode,
-                                   const int32_t* __restrict__ next_branch, int64_t nn, NodeRec* __restrict__ rec) {
+                                   const int32_t* __restrict__ next_branch, const int32_t* __restrict__ dfs, int64_t nn,
+                                   NodeRec* __restrict__ rec) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nn) return;
     NodeRec r;
@@ -503,12 +506,14 @@ __global__ void build_walk_records(const double* __restrict__ nmass, const doubl
         const double ch = __dmul_rn(csep, fmax(hmax[i], 0.0));
         r.gate2 = __dmul_rn(ch, ch);
     }
-    r.next_branch = next_branch[i];
+    r.next_branch = next_branch[i] < 0 ? -1 : dfs[next_branch[i]];
     if (nmass[i] == 0.0) { r.kind = -2; r.first = -1; }          // tree.rs:1087-1090
     else if (nchild[i] == 0) { r.kind = (int32_t)count[i]; r.first = (int32_t)start[i]; }
-    else { r.kind = -1; r.first = first_subnode[i]; }
+    else { r.kind = -1; r.first = dfs[first_subnode[i]]; }  // == dfs[i] + 1
     r.nleaf = 1;
-    rec[i] = r;
+    r.ref = (int32_t)i;
+    r.pad_ = 0;
+    rec[dfs[i]] = r;
 }
 // Leaf runs (tree.cuh) + the fp32 walk sources. One thread per sibling block (= per internal node, plus the root when
 // the root itself is a leaf): merges every maximal run of consecutive non-zero-mass leaf children into the record of
@@ -518,8 +523,8 @@ __global__ void merge_leaf_runs(const uint8_t* __restrict__ nchild, const int32_
                                 const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
                                 const int32_t* __restrict__ next_branch, const double* __restrict__ nmass,
                                 const double* __restrict__ ncom, const double* __restrict__ spos,
-                                const double* __restrict__ smass, int64_t nn, NodeRec* __restrict__ rec,
-                                float4* __restrict__ src32) {
+                                const double* __restrict__ smass, const int32_t* __restrict__ dfs, int64_t nn,
+                                NodeRec* __restrict__ rec, float4* __restrict__ src32) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nn) return;
     int64_t c0, c1;  // the sibling block [c0, c1)
@@ -541,12 +546,12 @@ __global__ void merge_leaf_runs(const uint8_t* __restrict__ nchild, const int32_
         }
         ox /= nl; oy /= nl; oz /= nl;
         if (nl > 1) {
-            NodeRec r = rec[j];
+            NodeRec r = rec[dfs[j]];  // sibling leaves are consecutive in depth-first order too (no descendants between)
             r.com[0] = ox; r.com[1] = oy; r.com[2] = oz;
             r.kind = (int32_t)total;
-            r.next_branch = next_branch[e - 1];
+            r.next_branch = next_branch[e - 1] < 0 ? -1 : dfs[next_branch[e - 1]];
             r.nleaf = nl;
-            rec[j] = r;
+            rec[dfs[j]] = r;
         }
         if (src32) {
             const uint32_t s0 = start[j];
@@ -557,19 +562,20 @@ __global__ void merge_leaf_runs(const uint8_t* __restrict__ nchild, const int32_
         j = e;
     }
 }
-__global__ void update_gates(const double* __restrict__ hmax, double csep, int64_t nn, NodeRec* __restrict__ rec) {
+__global__ void update_gates(const double* __restrict__ hmax, double csep, const int32_t* __restrict__ dfs, int64_t nn,
+                             NodeRec* __restrict__ rec) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nn) return;
     const double ch = __dmul_rn(csep, fmax(hmax[i], 0.0));
-    rec[i].gate2 = __dmul_rn(ch, ch);
+    rec[dfs[i]].gate2 = __dmul_rn(ch, ch);
 }
 // fp32 walk records from the float64 moments (layout: multipole.cuh, m2p_fast)
-__global__ void pack_walk_moments(const double* __restrict__ mom, int64_t nn, int order, int K, int rec,
-                                  float* __restrict__ out) {
+__global__ void pack_walk_moments(const double* __restrict__ mom, const int32_t* __restrict__ dfs, int64_t nn, int order,
+                                  int K, int rec, float* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nn) return;
     const double* m = mom + i * K;
-    float* o = out + i * rec;
+    float* o = out + (int64_t)dfs[i] * rec;  // fp32 records follow the walk records' depth-first order
     using namespace mp;
     if (order <= 1) { o[0] = (float)m[I000]; return; }
     o[0] = (float)m[I000];
@@ -686,7 +692,7 @@ bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const KeyScratch& k, int 
             A.take(t.node_start, (size_t)nn); A.take(t.node_count, (size_t)nn);
             A.take(t.first_subnode, (size_t)nn); A.take(t.next_branch, (size_t)nn);
             A.take(t.path_hi, (size_t)nn); A.take(t.path_lo, (size_t)nn);
-            A.take(t.node_nchild, (size_t)nn); A.take(t.level_ids, (size_t)nn);
+            A.take(t.node_nchild, (size_t)nn); A.take(t.level_ids, (size_t)nn); A.take(t.dfs_of_ref, (size_t)nn);
             if (pass == 0) A.commit(s);
         }
         f = FinalArrays{t.center.p, t.half.p, t.node_depth.p, t.node_start.p, t.node_count.p, t.first_subnode.p,
@@ -695,6 +701,7 @@ bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const KeyScratch& k, int 
     if (n == 0) {  // the reference's empty tree: one root leaf (tree.rs:658-734 with no points)
         layout_final(1);
         PNBX_LAUNCH(empty_root, 1, 1, 0, s, root4, f);
+        PNBX_CUDA(cudaMemsetAsync(t.dfs_of_ref.p, 0, 4, s));
         t.n_leaves = 1; t.depth = 0; t.n_internal = 0;
         t.ilevel_off.assign(2, 0);
         return true;
@@ -771,7 +778,7 @@ bool build_topology(pnbx_tree_impl& t, cudaStream_t s, const KeyScratch& k, int 
     PNBX_LAUNCH(child_counts, nblk(nn), 256, 0, s, d.mask, nn, nchild);
     exclusive_sum(nchild, scan, nn, s);
     PNBX_LAUNCH(assign_ref_ids, nblk(nn), 256, 0, s, d.parent, d.digit, d.mask, scan, nn, ref);
-    PNBX_LAUNCH(scatter_nodes, nblk(nn), 256, 0, s, d, scan, ref, k.base, nn, n, f, sortkey, sortval);
+    PNBX_LAUNCH(scatter_nodes, nblk(nn), 256, 0, s, d, scan, ref, k.base, nn, n, f, sortkey, sortval, t.dfs_of_ref.p);
     // internal nodes grouped by level (bottom-up payload sweeps): stable 7-bit sort of the DFS list
     PNBX_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, sortkey, key_out, sortval, t.level_ids.p, (int)nn, 0, 7, s));
     ++launch_counter();
@@ -844,6 +851,7 @@ pnbx_tree_impl::~pnbx_tree_impl() {
     key_hi.release(); key_lo.release(); perm.release(); src32.release(); sh32.release();
     node_depth.release(); node_nchild.release(); node_start.release(); node_count.release();
     first_subnode.release(); next_branch.release(); path_hi.release(); path_lo.release(); level_ids.release();
+    dfs_of_ref.release();
     moments32.release(); rec.release();
     a_payload.release(); a_topo.release(); a_src.release();
     if (ready) cudaEventDestroy(ready);
@@ -936,11 +944,12 @@ void tree_build_mass(pnbx_tree_impl& t, StageTimer& tm) {
     tm.begin("octree.payload.walk_records");
     PNBX_LAUNCH(build_walk_records, nblk(nn), 256, 0, s, t.nmass.p, t.ncom.p, t.half.p, t.has_hmax ? t.hmax.p : nullptr,
                 t.kernel == PNBX_KERNEL_SPLINE ? 1.0 : 2.8, t.node_nchild.p, t.node_start.p, t.node_count.p,
-                t.first_subnode.p, t.next_branch.p, nn, t.rec.p);
+                t.first_subnode.p, t.next_branch.p, t.dfs_of_ref.p, nn, t.rec.p);
     PNBX_LAUNCH(merge_leaf_runs, nblk(nn), 256, 0, s, t.node_nchild.p, t.first_subnode.p, t.node_start.p, t.node_count.p,
-                t.next_branch.p, t.nmass.p, t.ncom.p, t.spos.p, t.has_mass ? t.smass.p : nullptr, nn, t.rec.p,
-                t.n > 0 ? t.src32.p : nullptr);
-    PNBX_LAUNCH(pack_walk_moments, nblk(nn), 256, 0, s, t.moments.p, nn, t.order, t.n_moments, t.rec32, t.moments32.p);
+                t.next_branch.p, t.nmass.p, t.ncom.p, t.spos.p, t.has_mass ? t.smass.p : nullptr, t.dfs_of_ref.p, nn,
+                t.rec.p, t.n > 0 ? t.src32.p : nullptr);
+    PNBX_LAUNCH(pack_walk_moments, nblk(nn), 256, 0, s, t.moments.p, t.dfs_of_ref.p, nn, t.order, t.n_moments, t.rec32,
+                t.moments32.p);
     PNBX_CUDA(cudaGetLastError());
     t.has_payload = true;
     tm.end();
@@ -1171,7 +1180,7 @@ extern "C" int pnbx_tree_set_kernel(pnbx_tree* tp, int kernel) {
             if (t.kernel != kernel && t.has_payload && t.has_hmax) {  // the gate factor c depends on the kernel (kernel.rs:20-28)
                 PNBX_CUDA(cudaSetDevice(t.device));
                 PNBX_LAUNCH(update_gates, nblk(t.nn), 256, 0, t.stream, t.hmax.p, kernel == PNBX_KERNEL_SPLINE ? 1.0 : 2.8,
-                            t.nn, t.rec.p);
+                            t.dfs_of_ref.p, t.nn, t.rec.p);
                 PNBX_CUDA(cudaGetLastError());
                 tree_mark_ready(t);  // stream-ordered: evaluations wait for `ready`
             }

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
                 if (WANT & PNBX_WANT_POT) P += (double)pot;
                 if (WANT & PNBX_WANT_ACC) { Ax += (double)ax; Ay += (double)ay; Az += (double)az; }
             } else {
-                const T* M = a.moments + (int64_t)idx * a.K;
+                const T* M = a.moments + (int64_t)c.ref * a.K;  // float64 payloads are in the reference numbering
                 T D[mp::NCOEF];
                 mp::derivatives<DORD, T>((T)dx, (T)dy, (T)dz, tiny_v<T>(), D);
                 if (ORDER <= 1) {
