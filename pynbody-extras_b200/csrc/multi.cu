@@ -312,7 +312,7 @@ bool multi_tree_eval(pnbx_tree_impl& primary, const double* tgt_pos, int64_t m, 
     auto part = [&](int r) -> pnbx_tree_impl& { return r == 0 ? primary : *primary.replicas[(size_t)r - 1]; };
     const std::vector<int64_t> ob = even_bounds(m, W);  // slice of the caller's arrays that rank r returns
     OutSlices slices{};
-    slices.n = self ? W : 0;
+    slices.n = W;
     for (int r = 0; r <= W; ++r) slices.bounds[r] = ob[(size_t)r];
     std::vector<cudaEvent_t> alloc_ready((size_t)W, nullptr), walk_done((size_t)W, nullptr);
     HostBarrier bar(W);
@@ -327,31 +327,31 @@ bool multi_tree_eval(pnbx_tree_impl& primary, const double* tgt_pos, int64_t m, 
         DevBuf<double> dpot, dacc, tgt;
         if (want & PNBX_WANT_POT) dpot.alloc((size_t)std::max<int64_t>(cnt, 1), s);
         if (want & PNBX_WANT_ACC) dacc.alloc((size_t)std::max<int64_t>(3 * cnt, 1), s);
-        tree_begin_use(t, s);
-        if (self) {
-            // block-cyclic tree-order shard; results go straight to the owner of the particle's original index
-            slices.pot[r] = dpot.p;
-            slices.acc[r] = dacc.p;
-            PNBX_CUDA(cudaEventRecord(c.ev, s));
-            alloc_ready[(size_t)r] = c.ev;
-            bar.arrive_and_wait();
-            for (int p = 0; p < W; ++p)
-                if (p != r) PNBX_CUDA(cudaStreamWaitEvent(s, alloc_ready[(size_t)p], 0));  // peers' slices exist
-            ex.tree_order = ex.block_cyclic = true;
-            ex.shard_rank = r; ex.shard_world = W; ex.shard_block = 4096;
-            const int64_t mr = pnbx_shard_count(t.n, ex.shard_block, W, r);
-            const OutSlices sl = slices;  // complete after the barrier
-            if (mr > 0) tree_walk(t, ex, nullptr, mr, 0, theta, want, nullptr, nullptr, tm, nullptr, &sl);
-            PNBX_CUDA(cudaEventRecord(c.ev2, s));
-            walk_done[(size_t)r] = c.ev2;
-            bar.arrive_and_wait();
-            for (int p = 0; p < W; ++p)
-                if (p != r) PNBX_CUDA(cudaStreamWaitEvent(s, walk_done[(size_t)p], 0));  // everybody stored into my slice
-        } else if (cnt) {
-            tgt.alloc((size_t)3 * cnt, s);
-            copy_h2d(tgt.p, tgt_pos + 3 * lo, (size_t)cnt * 3 * sizeof(double), ex);
-            tree_walk(t, ex, tgt.p, cnt, 0, theta, want, dpot.p, dacc.p, tm, nullptr, nullptr);
+        if (!self) {  // every device holds all query points: it walks a balanced share of their path-key order
+            tgt.alloc((size_t)3 * m, s);
+            copy_h2d(tgt.p, tgt_pos, (size_t)m * 3 * sizeof(double), ex);
         }
+        tree_begin_use(t, s);
+        // results go straight to the device that owns the particle's / point's ORIGINAL index (peer stores)
+        slices.pot[r] = dpot.p;
+        slices.acc[r] = dacc.p;
+        PNBX_CUDA(cudaEventRecord(c.ev, s));
+        alloc_ready[(size_t)r] = c.ev;
+        bar.arrive_and_wait();
+        for (int p = 0; p < W; ++p)
+            if (p != r) PNBX_CUDA(cudaStreamWaitEvent(s, alloc_ready[(size_t)p], 0));  // peers' slices exist
+        ex.block_cyclic = true;
+        ex.tree_order = self;
+        ex.shard_rank = r; ex.shard_world = W;
+        ex.shard_block = self ? 4096 : 256;  // tree-order particles / path-key-ordered query points
+        const int64_t mr = pnbx_shard_count(m, ex.shard_block, W, r);
+        const OutSlices sl = slices;  // complete after the barrier
+        if (mr > 0) tree_walk(t, ex, self ? nullptr : tgt.p, self ? mr : m, 0, theta, want, nullptr, nullptr, tm, nullptr, &sl);
+        PNBX_CUDA(cudaEventRecord(c.ev2, s));
+        walk_done[(size_t)r] = c.ev2;
+        bar.arrive_and_wait();
+        for (int p = 0; p < W; ++p)
+            if (p != r) PNBX_CUDA(cudaStreamWaitEvent(s, walk_done[(size_t)p], 0));  // everybody stored into my slice
         tree_end_use(t, s);
         if (cnt) {
             if (want & PNBX_WANT_POT) copy_d2h(out_pot + lo, dpot.p, (size_t)cnt * sizeof(double), ex);

@@ -194,7 +194,9 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
             oslot = a.tree_order ? k : (int64_t)a.perm[s] - a.tgt_begin;
             if (a.sh) { th64 = a.sh[s]; has_th = true; }  // target_h_opt = softenings[i] (tree.rs:1439)
         } else {
-            const uint32_t q = a.torder[k];
+            // walk order = path-key order of the query points; a multi-device call takes a block-cyclic share of it
+            const int64_t sp = a.cyc_block > 0 ? ((k / a.cyc_block) * a.cyc_world + a.cyc_rank) * a.cyc_block + k % a.cyc_block : k;
+            const uint32_t q = a.torder[sp];
             tx = a.tgt[3 * (int64_t)q]; ty = a.tgt[3 * (int64_t)q + 1]; tz = a.tgt[3 * (int64_t)q + 2];
             oslot = q;
         }
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
         double* op = a.out_pot;
         double* oa = a.out_acc;
         if (a.slices.n > 0) {  // the slice (a peer GPU's memory, or ours) that owns this particle's original index
-            const int64_t gi = (int64_t)a.perm[skip];
+            const int64_t gi = a.self ? (int64_t)a.perm[skip] : oslot;  // original particle index / query point index
             int o = 0;
             while (o + 1 < a.slices.n && gi >= a.slices.bounds[o + 1]) ++o;
             oslot = gi - a.slices.bounds[o];
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
 
 template <class T, int SMODE>
 void launch_walk(int order, int want, const WalkArgs<T>& a, cudaStream_t s) {
-    const unsigned grid = (unsigned)ceil_div(a.m, WT);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, ceil_div(a.m, WT));
 #define PNBX_W(O, W)                                                        \
     if (order == O && want == W) {                                          \
         PNBX_LAUNCH((walk_kernel<O, W, T, SMODE>), grid, WT, 0, s, a);      \
@@ -455,6 +457,10 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
                const OutSlices* slices) {
     cudaStream_t s = ex.stream;
     const bool self = d_tgt == nullptr;
+    // query points of a multi-device call: `m` points are sorted by path key on every device (identical order) and this
+    // device walks its block-cyclic share of that order (balanced whatever the layout of the caller's array)
+    const bool pts_cyclic = !self && ex.block_cyclic;
+    const int64_t m_walk = pts_cyclic ? pnbx_shard_count(m, ex.shard_block, ex.shard_world, ex.shard_rank) : m;
     DevBuf<uint32_t> tlist, torder;
     tm.begin("octree.walk.prepare_targets");
     const bool tree_order = self && ex.tree_order;
@@ -500,10 +506,10 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         a.spos = t.spos.p; a.smass = t.has_mass ? t.smass.p : nullptr;
         a.sh = t.has_h ? t.sh.p : nullptr;
         a.perm = t.perm.p;
-        a.m = m; a.self = self ? 1 : 0;
+        a.m = m_walk; a.self = self ? 1 : 0;
         a.tlist = tlist.p; a.tgt_begin = tgt_begin; a.tgt = d_tgt; a.torder = torder.p;
         a.tree_order = tree_order ? 1 : 0;
-        a.cyc_block = (tree_order && ex.block_cyclic) ? ex.shard_block : 0;
+        a.cyc_block = ((tree_order && ex.block_cyclic) || pts_cyclic) ? ex.shard_block : 0;
         a.cyc_rank = ex.shard_rank; a.cyc_world = ex.shard_world;
         a.theta2 = theta * theta;
         a.rc = t.root4.p;
@@ -518,7 +524,7 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         WalkArgs<double> a;
         fill(a);
         a.moments = t.moments.p; a.K = t.n_moments; a.src = nullptr; a.src_h = t.has_h ? t.sh.p : nullptr;
-        PNBX_LAUNCH((walk_kernel<1, 0, double, 3>), (unsigned)ceil_div(m, WT), WT, 0, s, a);
+        PNBX_LAUNCH((walk_kernel<1, 0, double, 3>), (unsigned)std::max<int64_t>(1, ceil_div(m_walk, WT)), WT, 0, s, a);
     } else if (ex.f64) {
         WalkArgs<double> a;
         fill(a);
