@@ -32,7 +32,7 @@ def main():
     if args.set == "nfw":
         pos, m, h = synthetic.nfw_disc(args.n, seed=3)
     elif args.set == "zoom":
-        pos, m, h = synthetic.zoom_families(args.n, seed=4)
+        pos, m, h = synthetic.zoom_set(args.n, seed=4)
     elif args.set == "hernquist":
         pos, m = synthetic.hernquist(args.n, seed=2)
         h = np.full(args.n, 0.01)

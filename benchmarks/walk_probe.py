@@ -6,12 +6,12 @@ for p in (os.path.join(ROOT, "pynbody-extras_b200"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 import torch  # noqa: E402
-from benchmarks.synthetic import nfw_disc, zoom_families  # noqa: E402
+from benchmarks.synthetic import nfw_disc, zoom_set  # noqa: E402
 from pynbodyext.gravity import device as gdev  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 which = sys.argv[2] if len(sys.argv) > 2 else "nfw"
 orders = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [3]
-pos, m, h = nfw_disc(n, seed=3) if which == "nfw" else zoom_families(n, seed=4)
+pos, m, h = nfw_disc(n, seed=3) if which == "nfw" else zoom_set(n, seed=4)
 d = torch.device("cuda", 0)
 dp, dm, dh = (torch.from_numpy(a).to(d) for a in (pos, m, h))
 for order in orders:

@@ -358,6 +358,276 @@ def translate_multipole(env, child, shift, order):
     return out
 
 
+
+# ------------------------------------------------------------------------------------------ tree.rs, second restatement
+def fma(a, b, c):
+    """f64::mul_add: exactly rounded a*b + c (rational arithmetic, then one rounding)."""
+    from fractions import Fraction
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+class PyOctree:
+    """tree.rs re-stated in Python, independently of oracle/gravity_oracle.cpp: the CONTROL FLOW (recursive bucket
+    build :804-864, walk links :736-776, reverse payload sweeps :866-965 / :1014-1067, stackless traversal with the
+    leaf-before-opening rule, zero-mass skip and the hmax softening gate :55-71 / :1069-1370, leaf sums :97-417, entry
+    points :1415-1558) is written here by hand; every formula it evaluates (kernels, P2M, M2M, derivative tensors,
+    evaluators) is the mechanically translated reference source. The dead "constant target softening" fast path of
+    leaf_potential_sum (:122-171, unreachable through the entry points) is not restated."""
+    NONE = -1
+
+    def __init__(self, env, pos, mass, h, leaf_capacity, order, kernel):
+        self.env, self.pos, self.mass, self.h = env, pos, mass, h
+        self.cap, self.order_raw, self.kernel = max(int(leaf_capacity), 1), int(order), kernel
+        n = len(pos)
+        mn = [math.inf] * 3
+        mx = [-math.inf] * 3
+        for p in pos:
+            for i in range(3):
+                if p[i] < mn[i]:
+                    mn[i] = p[i]
+                if p[i] > mx[i]:
+                    mx[i] = p[i]
+        center = [(mn[i] + mx[i]) / 2.0 for i in range(3)]
+        half = 0.0
+        for i in range(3):
+            half = max(half, (mx[i] - mn[i]) / 2.0)
+        if half == 0.0:
+            half = 1e-6
+        self.nodes = [self._node(center, half, list(range(n)))]
+        self._build(0)
+        self._links()
+
+    @staticmethod
+    def _node(center, half, indices):
+        s = half * 2.0
+        return {"center": list(center), "half": half, "size2": s * s, "children": None, "indices": indices}
+
+    def _subdivide(self, k):
+        nd = self.nodes[k]
+        center, half, parent = nd["center"], nd["half"], nd["indices"]
+        nd["indices"] = []
+        buckets = [[] for _ in range(8)]
+        for pi in parent:
+            p = self.pos[pi]
+            oct_ = (1 if p[0] >= center[0] else 0) | (2 if p[1] >= center[1] else 0) | (4 if p[2] >= center[2] else 0)
+            buckets[oct_].append(pi)
+        child = [self.NONE] * 8
+        for o in range(8):
+            if not buckets[o]:
+                continue
+            cc = list(center)
+            off = half / 2.0
+            cc[0] += off if o & 1 else -off
+            cc[1] += off if o & 2 else -off
+            cc[2] += off if o & 4 else -off
+            child[o] = len(self.nodes)
+            self.nodes.append(self._node(cc, off, buckets[o]))
+        nd["children"] = child
+
+    def _build(self, k):
+        import sys as _sys
+        _sys.setrecursionlimit(10000)
+        if not len(self.nodes[k]["indices"]) > self.cap:
+            return
+        self._subdivide(k)
+        for c in self.nodes[k]["children"]:
+            if c != self.NONE:
+                self._build(c)
+
+    def _links(self):
+        n = len(self.nodes)
+        self.first, self.next = [self.NONE] * n, [self.NONE] * n
+
+        def rec(k):
+            ch = self.nodes[k]["children"]
+            if ch is None:
+                return
+            last = None
+            for c in ch:
+                if c == self.NONE:
+                    continue
+                if self.first[k] == self.NONE:
+                    self.first[k] = c
+                if last is not None:
+                    self.next[last] = c
+                last = c
+            if last is not None:
+                self.next[last] = self.next[k]
+            for c in ch:
+                if c != self.NONE and self.nodes[c]["children"] is not None:
+                    rec(c)
+        rec(0)
+
+    def build_mass(self):
+        env, nn = self.env, len(self.nodes)
+        self.bh_mass, self.bh_com = [0.0] * nn, [[0.0] * 3 for _ in range(nn)]
+        for k in reversed(range(nn)):
+            mass, com, nd = 0.0, [0.0, 0.0, 0.0], self.nodes[k]
+            if nd["children"] is None:
+                if nd["indices"]:
+                    for pi in nd["indices"]:
+                        p = self.pos[pi]
+                        if self.mass is not None:
+                            m = self.mass[pi]
+                            mass += m
+                            com[0] += p[0] * m; com[1] += p[1] * m; com[2] += p[2] * m
+                        else:
+                            mass += 1.0
+                            com[0] += p[0]; com[1] += p[1]; com[2] += p[2]
+                    if mass > 0.0:
+                        com = [c / mass for c in com]
+            else:
+                for c in nd["children"]:
+                    if c == self.NONE or self.bh_mass[c] == 0.0:
+                        continue
+                    cm, cc = self.bh_mass[c], self.bh_com[c]
+                    mass += cm
+                    com[0] += cc[0] * cm; com[1] += cc[1] * cm; com[2] += cc[2] * cm
+                if mass > 0.0:
+                    com = [c / mass for c in com]
+            self.bh_mass[k], self.bh_com[k] = mass, com
+        self.hmax = None
+        if self.h is not None:
+            self.hmax = [0.0] * nn
+            for k in reversed(range(nn)):
+                nd, m = self.nodes[k], 0.0
+                if nd["children"] is None:
+                    for pi in nd["indices"]:
+                        m = max(m, max(self.h[pi], 0.0))
+                else:
+                    for c in nd["children"]:
+                        if c != self.NONE:
+                            m = max(m, self.hmax[c])
+                self.hmax[k] = m
+        self.moments = None
+        if self.order_raw > 0:
+            order = min(self.order_raw, 5)
+            F = env["FIELDS"]
+            mom = [env["new_moment"]() for _ in range(nn)]
+            for k in reversed(range(nn)):
+                nd = self.nodes[k]
+                if self.bh_mass[k] == 0.0:
+                    continue
+                if nd["children"] is None:
+                    if not nd["indices"]:
+                        continue
+                    mom[k] = env["from_points"](order, self.pos, self.mass, nd["indices"], self.bh_com[k])
+                else:
+                    acc = env["new_moment"]()
+                    for c in nd["children"]:
+                        if c == self.NONE or self.bh_mass[c] == 0.0:
+                            continue
+                        shift = [self.bh_com[k][i] - self.bh_com[c][i] for i in range(3)]
+                        tr = translate_multipole(env, mom[c], shift, order)
+                        for f in F:  # add_assign, field by field in struct order
+                            setattr(acc, f, getattr(acc, f) + getattr(tr, f))
+                    mom[k] = acc
+            self.moments = mom
+
+    # ---- traversal
+    def _soft_ok(self, k, dist2, th):
+        if self.hmax is None:
+            return True
+        hh = max(self.hmax[k], 0.0)
+        if th is not None:
+            hh = max(hh, max(th, 0.0))
+        if hh <= 0.0:
+            return True
+        ch = (2.8 if self.kernel == 0 else 1.0) * hh
+        return dist2 > ch * ch
+
+    def _leaf(self, indices, t, skip, th, acc_mode, out):
+        env = self.env
+        target_h = max(th if th is not None else 0.0, 0.0)
+        use_soft = self.h is not None or target_h > 0.0
+        spline = self.kernel == 1
+        for pi in indices:
+            if pi == skip:
+                continue
+            p = self.pos[pi]
+            dx, dy, dz = p[0] - t[0], p[1] - t[1], p[2] - t[2]
+            r2 = fma(dx, dx, fma(dy, dy, dz * dz))
+            m = self.mass[pi] if self.mass is not None else 1.0
+            newton = True
+            hh = 0.0
+            if use_soft:
+                hh = max(max(self.h[pi], 0.0), target_h) if self.h is not None else target_h
+                newton = hh <= 0.0 or (spline and r2 >= hh * hh)
+            if not acc_mode:
+                if newton:
+                    inv_r = 1.0 / math.sqrt(r2 + R2_TINY)
+                    out[0] += (-m * inv_r) if (use_soft or self.mass is not None) else -inv_r
+                else:
+                    out[0] += m * kernel_potential_per_unit_mass(env, self.kernel, math.sqrt(r2 + R2_TINY), hh)
+            else:
+                if newton:
+                    inv_r = 1.0 / math.sqrt(r2 + R2_TINY)
+                    inv_r3 = (inv_r * inv_r) * inv_r
+                    if use_soft or self.mass is not None:
+                        out[0] += m * dx * inv_r3; out[1] += m * dy * inv_r3; out[2] += m * dz * inv_r3
+                    else:
+                        out[0] += dx * inv_r3; out[1] += dy * inv_r3; out[2] += dz * inv_r3
+                else:
+                    g = kernel_accel_factor(env, self.kernel, math.sqrt(r2 + R2_TINY), hh)
+                    out[0] += m * dx * g; out[1] += m * dy * g; out[2] += m * dz * g
+
+    def walk(self, t, skip, th, theta, acc_mode):
+        env = self.env
+        out = [0.0, 0.0, 0.0] if acc_mode else [0.0]
+        soft_en = self.hmax is not None or th is not None
+        theta2 = theta * theta
+        visits = accepts = 0
+        k = 0
+        while k != self.NONE:
+            visits += 1
+            if self.bh_mass[k] == 0.0:
+                k = self.next[k]
+                continue
+            nd = self.nodes[k]
+            if nd["children"] is None:
+                self._leaf(nd["indices"], t, skip, th, acc_mode, out)
+                k = self.next[k]
+                continue
+            com = self.bh_com[k]
+            dx, dy, dz = com[0] - t[0], com[1] - t[1], com[2] - t[2]
+            dist2 = fma(dx, dx, fma(dy, dy, dz * dz)) + R2_TINY
+            ok = self._soft_ok(k, dist2, th) if soft_en else True
+            if ok and nd["size2"] < theta2 * dist2:
+                accepts += 1
+                if self.moments is None:
+                    inv_r = 1.0 / math.sqrt(dist2 + R2_TINY)
+                    M = self.bh_mass[k]
+                    if acc_mode:
+                        inv_r3 = (inv_r * inv_r) * inv_r
+                        out[0] += M * dx * inv_r3; out[1] += M * dy * inv_r3; out[2] += M * dz * inv_r3
+                    else:
+                        out[0] += -M * inv_r
+                else:
+                    o = min(self.order_raw, 5)
+                    if o <= 1:
+                        d, sfx = env["derivs1"](dx, dy, dz, R2_TINY), "o0_d1"
+                    elif o <= 4:
+                        d, sfx = env[f"derivs{o}"](dx, dy, dz, R2_TINY), f"o{o}_d{o}"
+                    else:
+                        d, sfx = env["derivs_generic"](dx, dy, dz, R2_TINY, 5), None
+                    mm = self.moments[k]
+                    if acc_mode:
+                        a = env["gravity_accel_multipole"](mm, d, 5) if sfx is None else env["gravity_accel_multipole_" + sfx](mm, d)
+                        out[0] += a[0]; out[1] += a[1]; out[2] += a[2]
+                    else:
+                        out[0] += env["gravity_potential_multipole"](mm, d, 5) if sfx is None else env["gravity_potential_multipole_" + sfx](mm, d)
+                k = self.next[k]
+            else:
+                k = self.first[k]
+        return out, visits, accepts
+
+    def compute(self, theta, acc_mode):
+        return [self.walk(self.pos[i], i, None if self.h is None else self.h[i], theta, acc_mode)[0] for i in range(len(self.pos))]
+
+    def at_points(self, pts, theta, acc_mode):
+        return [self.walk(p, self.NONE, None, theta, acc_mode)[0] for p in pts]
+
+
 def kernel_potential_per_unit_mass(env, kind, r, h):
     """kernel.rs:41-56 (the `match kind` wrapper around w2)."""
     if r == 0.0:
@@ -468,6 +738,57 @@ def main():
             out[f"direct_{tag}_k{kind}_pot_pts"] = np.array(env["direct_potentials_kernel_at_points"](P, Mv, Hv, T, kind))
             out[f"direct_{tag}_k{kind}_acc_pts"] = np.array(env["direct_accelerations_kernel_at_points"](P, Mv, Hv, T, kind))
             out[f"direct_{tag}_k{kind}_pot_noh"] = np.array(env["direct_potentials_kernel"](P, Mv, None, kind))
+    # ---- tree.rs through the independent Python restatement (PyOctree): small clustered sets, every order, both kernels,
+    # per-particle softenings (incl. zero / negative), unit masses, a zero-mass clump (subtree skip), theta 0.7 and 0
+    def tree_case(tag, n, cap, order, kernel, with_h, with_mass, theta, zero_clump=False):
+        import zlib
+        r_ = np.random.default_rng(zlib.crc32(tag.encode()))
+        rr = 0.3 / np.sqrt(np.maximum(r_.uniform(0, 0.99, n), 1e-9) ** (-2.0 / 3.0) - 1.0)
+        v = r_.normal(size=(n, 3))
+        pos_t = rr[:, None] * v / np.linalg.norm(v, axis=1)[:, None] + np.array([0.1, -0.2, 0.05])
+        mass_t = (0.5 + r_.random(n)) if with_mass else None
+        if zero_clump and mass_t is not None:
+            sel = np.argsort(np.linalg.norm(pos_t - pos_t[0], axis=1))[:40]
+            mass_t[sel] = 0.0
+        h_t = r_.uniform(-0.01, 0.08, n) if with_h else None
+        if h_t is not None:
+            h_t[::7] = 0.0
+        pts = r_.uniform(-0.6, 0.6, (9, 3))
+        t = PyOctree(env, pos_t.tolist(), None if mass_t is None else mass_t.tolist(), None if h_t is None else h_t.tolist(),
+                     cap, order, kernel)
+        t.build_mass()
+        nn = len(t.nodes)
+        out[f"tree_{tag}_pos"] = pos_t
+        out[f"tree_{tag}_mass"] = mass_t if mass_t is not None else np.zeros(0)
+        out[f"tree_{tag}_h"] = h_t if h_t is not None else np.zeros(0)
+        out[f"tree_{tag}_pts"] = pts
+        out[f"tree_{tag}_params"] = np.array([cap, order, kernel, theta], dtype=np.float64)
+        out[f"tree_{tag}_center"] = np.array([nd["center"] for nd in t.nodes])
+        out[f"tree_{tag}_half"] = np.array([nd["half"] for nd in t.nodes])
+        out[f"tree_{tag}_first"] = np.array(t.first, dtype=np.int64)
+        out[f"tree_{tag}_next"] = np.array(t.next, dtype=np.int64)
+        out[f"tree_{tag}_leaf_count"] = np.array([-1 if nd["children"] is not None else len(nd["indices"]) for nd in t.nodes], dtype=np.int64)
+        out[f"tree_{tag}_leaf_particles"] = np.array([pi for nd in t.nodes if nd["children"] is None for pi in nd["indices"]], dtype=np.int64)
+        out[f"tree_{tag}_bh_mass"] = np.array(t.bh_mass)
+        out[f"tree_{tag}_bh_com"] = np.array(t.bh_com)
+        if t.hmax is not None:
+            out[f"tree_{tag}_hmax"] = np.array(t.hmax)
+        if t.moments is not None:
+            out[f"tree_{tag}_moments"] = np.array([[getattr(m_, f) for f in F] for m_ in t.moments])
+        out[f"tree_{tag}_pot"] = np.array(t.compute(theta, False)).ravel()
+        out[f"tree_{tag}_acc"] = np.array(t.compute(theta, True))
+        out[f"tree_{tag}_pot_pts"] = np.array(t.at_points(pts.tolist(), theta, False)).ravel()
+        out[f"tree_{tag}_acc_pts"] = np.array(t.at_points(pts.tolist(), theta, True))
+        return nn
+
+    cases = [("o0_plain", 260, 8, 0, 0, False, True, 0.7, False), ("o1_unit", 200, 4, 1, 0, False, False, 0.7, False),
+             ("o2_spline", 300, 8, 2, 1, True, True, 0.7, False), ("o3_spline", 400, 8, 3, 1, True, True, 0.7, True),
+             ("o3_plummer", 300, 6, 3, 0, True, True, 0.5, False), ("o4_spline", 240, 8, 4, 1, True, True, 0.7, False),
+             ("o5_plummer", 240, 5, 5, 0, True, True, 0.7, False), ("o3_theta0", 120, 3, 3, 1, True, True, 0.0, False),
+             ("o3_cap1", 150, 1, 3, 1, True, True, 0.8, False)]
+    out["tree_cases"] = np.array([c[0] for c in cases])
+    for c in cases:
+        tree_case(*c)
     out["field_order"] = np.array(F)
     out["deriv_field_order"] = np.array(D)
     path = os.path.join(HERE, "reference_exec.npz")

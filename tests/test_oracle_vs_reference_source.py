@@ -148,3 +148,52 @@ def test_gpu_direct_against_reference_source_goldens(tag):
         assert rel(r.direct_potentials_py(pos, m, 0, h, kind, precision="f32"), G[f"direct_{tag}_k{kind}_pot"]) < 1e-5
         assert rel(r.direct_accelerations_at_points_py(pos, tgt, m, 0, h, kind, precision="f32"),
                    G[f"direct_{tag}_k{kind}_acc_pts"]) < 1e-4
+
+
+# ---- tree.rs: the oracle against an INDEPENDENT second restatement of its control flow (PyOctree in
+# tests/golden/make_reference_exec.py) that evaluates the mechanically translated reference arithmetic. Bit-exact.
+TREE_CASES = [str(c) for c in G["tree_cases"]]
+
+
+def _oracle_tree(tag):
+    cap, order, kernel, theta = G[f"tree_{tag}_params"]
+    pos = G[f"tree_{tag}_pos"]
+    mass = G[f"tree_{tag}_mass"] if G[f"tree_{tag}_mass"].size else None
+    h = G[f"tree_{tag}_h"] if G[f"tree_{tag}_h"].size else None
+    t = O.Tree(pos, mass, int(cap), int(order), h, int(kernel) if h is not None else None)
+    if mass is None:
+        t.build_mass(None)  # gravity.rs:210-220 builds payloads only when masses are given; unit masses need build_mass()
+    return t, float(theta)
+
+
+@pytest.mark.parametrize("tag", TREE_CASES)
+def test_tree_topology_and_payload_bit_exact(tag):
+    t, _ = _oracle_tree(tag)
+    topo = t.topology()
+    assert np.array_equal(bits(topo["center"]), bits(G[f"tree_{tag}_center"]))
+    assert np.array_equal(bits(topo["half"]), bits(G[f"tree_{tag}_half"]))
+    assert np.array_equal(topo["first_subnode"], G[f"tree_{tag}_first"])
+    assert np.array_equal(topo["next_branch"], G[f"tree_{tag}_next"])
+    assert np.array_equal(topo["leaf_count"], G[f"tree_{tag}_leaf_count"])
+    ids = np.nonzero(topo["leaf_count"] >= 0)[0]
+    flat = np.concatenate([topo["leaf_particles"][topo["leaf_start"][i]:topo["leaf_start"][i] + topo["leaf_count"][i]] for i in ids])
+    assert np.array_equal(flat, G[f"tree_{tag}_leaf_particles"])
+    pay = t.payload()
+    assert np.array_equal(bits(pay["mass"]), bits(G[f"tree_{tag}_bh_mass"]))
+    assert np.array_equal(bits(pay["com"]), bits(G[f"tree_{tag}_bh_com"]))
+    if f"tree_{tag}_hmax" in G:
+        assert np.array_equal(bits(pay["hmax"]), bits(G[f"tree_{tag}_hmax"]))
+    if f"tree_{tag}_moments" in G:
+        k = pay["moments"].shape[1]  # compact storage keeps the first k coefficients (MultipoleMoments::from_full)
+        assert np.array_equal(bits(pay["moments"]), bits(G[f"tree_{tag}_moments"][:, :k]))
+
+
+@pytest.mark.parametrize("tag", TREE_CASES)
+def test_tree_walk_results_bit_exact(tag):
+    t, theta = _oracle_tree(tag)
+    p, a = t.eval(theta)
+    assert np.array_equal(bits(p), bits(G[f"tree_{tag}_pot"]))
+    assert np.array_equal(bits(a), bits(G[f"tree_{tag}_acc"]))
+    pq, aq = t.eval(theta, targets=G[f"tree_{tag}_pts"])
+    assert np.array_equal(bits(pq), bits(G[f"tree_{tag}_pot_pts"]))
+    assert np.array_equal(bits(aq), bits(G[f"tree_{tag}_acc_pts"]))
