@@ -376,7 +376,9 @@ def tree_1e8_section(args, rank, world, local, dev, barrier, gloo, peak_tf):
     c_lo, c_n = n // 2, 10_000
     p32, a32 = tree.eval(theta, 3, tgt_begin=c_lo, count=c_n)
     p64, a64 = tree.eval(theta, 3, tgt_begin=c_lo, count=c_n, precision="f64")
+    os.environ["PNBX_WPT_MAX_TARGETS"] = "0"  # the whole-array API call below runs the lane-per-target kernel
     p1_ref = tree.eval(theta, 1, tgt_begin=c_lo, count=c_n)[0].cpu().numpy()  # potentials-only kernel (what the API leg runs)
+    del os.environ["PNBX_WPT_MAX_TARGETS"]
     chk_fp = {"rms_rel_pot": rms((p32 - p64) / p64), "rms_rel_acc": rms((a32 - a64).norm(dim=1) / a64.norm(dim=1)),
               "targets": c_n, "tolerance": 1e-5}
     chk_fp["ok"] = bool(chk_fp["rms_rel_pot"] < 1e-5 and chk_fp["rms_rel_acc"] < 1e-5)

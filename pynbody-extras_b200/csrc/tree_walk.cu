@@ -421,6 +421,180 @@ void launch_walk(int order, int want, const WalkArgs<T>& a, cudaStream_t s) {
     throw ArgError{PNBX_ERR_ARG, "internal: no walk kernel variant"};
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Warp-per-target walk (fp32 arithmetic) for calls with FEW targets: query grids (rotation curves, binding-energy
+// profiles; BASELINE config 5) hand the lane-per-target kernel a few thousand warps whose cost is set by the heaviest
+// ones — a target in a softened core sums thousands of leaf particles serially while most of the GPU idles. Here one
+// warp owns one target: the traversal (same records, same float64 opening test and softening gate, so the
+// interaction list is again exactly the reference's) is warp-uniform, and the WORK it generates is spread over the
+// lanes through two 32-entry queues — accepted nodes (one M2P per lane) and leaf particles (one pair per lane) —
+// that are drained whenever they fill. Every lane folds its fp32 terms into float64 accumulators; one fixed-order
+// butterfly at the end adds the 32 partials. The result is a pure function of (tree, target).
+template <int ORDER, int WANT, int SMODE>
+__global__ void __launch_bounds__(WT) walk_wpt_kernel(const WalkArgs<float> a) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t k = ((int64_t)blockIdx.x * WT + threadIdx.x) >> 5;  // one target per warp
+    if (k >= a.m) return;  // whole warp
+    double tx, ty, tz, th64 = 0.0;
+    int skip = -1;
+    int64_t oslot;
+    bool has_th = false;
+    if (a.self) {
+        uint32_t s;
+        if (a.cyc_block > 0) s = (uint32_t)(((k / a.cyc_block) * a.cyc_world + a.cyc_rank) * a.cyc_block + k % a.cyc_block);
+        else s = a.tree_order ? (uint32_t)(a.tgt_begin + k) : a.tlist ? a.tlist[k] : (uint32_t)k;
+        tx = a.spos[3 * (int64_t)s]; ty = a.spos[3 * (int64_t)s + 1]; tz = a.spos[3 * (int64_t)s + 2];
+        skip = (int)s;
+        oslot = a.tree_order ? k : (int64_t)a.perm[s] - a.tgt_begin;
+        if (a.sh) { th64 = a.sh[s]; has_th = true; }
+    } else {
+        const int64_t sp = a.cyc_block > 0 ? ((k / a.cyc_block) * a.cyc_world + a.cyc_rank) * a.cyc_block + k % a.cyc_block : k;
+        const uint32_t q = a.torder[sp];
+        tx = a.tgt[3 * (int64_t)q]; ty = a.tgt[3 * (int64_t)q + 1]; tz = a.tgt[3 * (int64_t)q + 2];
+        oslot = q;
+    }
+    const float thc = (float)fmax(th64, 0.0);
+    const float th2 = thc * thc;
+    const bool spline = SMODE == 2;
+    double gate_t = 0.0;
+    if (SMODE != 0 && a.gated && has_th) {
+        const double ch = __dmul_rn(spline ? 1.0 : 2.8, fmax(th64, 0.0));
+        gate_t = __dmul_rn(ch, ch);
+    }
+    double P = 0.0, Ax = 0.0, Ay = 0.0, Az = 0.0;  // this lane's share
+    // queues: one pending accepted node / one pending leaf particle per lane
+    int qn_node = -1;
+    float qn_dx = 0.f, qn_dy = 0.f, qn_dz = 0.f;
+    int n_nodes = 0;
+    int qp_idx = -1;
+    float qp_lx = 0.f, qp_ly = 0.f, qp_lz = 0.f;
+    int n_parts = 0;
+
+    auto drain_nodes = [&]() {
+        if (qn_node >= 0) {
+            float pot = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+            const float* rec = reinterpret_cast<const float*>(a.moments) + (int64_t)qn_node * mp::fast_rec_floats(ORDER);
+            if (ORDER <= 3) mp::m2p_fast<(ORDER <= 3 ? ORDER : 3), WANT>(rec, qn_dx, qn_dy, qn_dz, pot, ax, ay, az);
+            else mp::m2p_fast45<(ORDER >= 4 ? ORDER : 4), WANT>(rec, qn_dx, qn_dy, qn_dz, pot, ax, ay, az);
+            if (WANT & PNBX_WANT_POT) P += (double)pot;
+            if (WANT & PNBX_WANT_ACC) { Ax += (double)ax; Ay += (double)ay; Az += (double)az; }
+        }
+        qn_node = -1;
+        n_nodes = 0;
+    };
+    auto drain_parts = [&]() {
+        if (qp_idx >= 0) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.src) + qp_idx);
+            const float dx = s4.x - qp_lx, dy = s4.y - qp_ly, dz = s4.z - qp_lz;
+            float r2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, FLT_MIN)));
+            float m = s4.w;
+            if (qp_idx == skip) {  // skip_self by index (tree.rs:130): contributes exactly nothing
+                m = 0.f;
+                r2 = 1e30f;
+            }
+            float kpot, kacc;
+            bool inside = false;
+            float h2 = 0.f;
+            if (SMODE != 0) {
+                h2 = fmaxf(__ldg(a.src_h + qp_idx), th2);
+                if (SMODE == 2) inside = r2 < h2;  // the lane-per-target kernel's predicate (d = r2 - h2 < 0)
+                else r2 += h2;
+            }
+            const float rinv = mp::inv_sqrt<float>(r2);
+            kpot = -rinv;
+            kacc = rinv * rinv * rinv;
+            if (SMODE == 2 && inside) {
+                const float hinv = mp::inv_sqrt<float>(h2);
+                w2_terms_f32(r2, rinv, h2 * hinv, hinv, kpot, kacc);
+            }
+            if (WANT & PNBX_WANT_POT) P += (double)(m * kpot);
+            if (WANT & PNBX_WANT_ACC) {
+                const float g = m * kacc;
+                Ax += (double)(dx * g); Ay += (double)(dy * g); Az += (double)(dz * g);
+            }
+        }
+        qp_idx = -1;
+        n_parts = 0;
+    };
+
+    int idx = 0;
+    while (idx >= 0) {
+        const NodeRec c = a.rec[idx];
+        if (c.kind == -2) { idx = c.next_branch; continue; }
+        if (c.kind >= 0) {  // leaf run: queue its particles, 32 at a time
+            const float lx = (float)(tx - c.com[0]), ly = (float)(ty - c.com[1]), lz = (float)(tz - c.com[2]);
+            int done = 0;
+            while (done < c.kind) {
+                const int room = 32 - n_parts;
+                const int take = min(room, c.kind - done);
+                if (lane >= n_parts && lane < n_parts + take) {
+                    qp_idx = c.first + done + (lane - n_parts);
+                    qp_lx = lx; qp_ly = ly; qp_lz = lz;
+                }
+                n_parts += take;
+                done += take;
+                if (n_parts == 32) drain_parts();
+            }
+            idx = c.next_branch;
+            continue;
+        }
+        const double dx = c.com[0] - tx, dy = c.com[1] - ty, dz = c.com[2] - tz;
+        const double dist2 = fma(dx, dx, fma(dy, dy, __dmul_rn(dz, dz)));
+        bool accept = c.size2 < __dmul_rn(a.theta2, dist2);
+        if (SMODE != 0) accept = accept && dist2 > c.gate2 && dist2 > gate_t;
+        if (accept) {
+            if (lane == n_nodes) { qn_node = idx; qn_dx = (float)dx; qn_dy = (float)dy; qn_dz = (float)dz; }
+            if (++n_nodes == 32) drain_nodes();
+            idx = c.next_branch;
+        } else {
+            idx = c.first;
+        }
+    }
+    drain_nodes();
+    drain_parts();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {  // fixed-order butterfly: deterministic
+        if (WANT & PNBX_WANT_POT) P += __shfl_xor_sync(FULL, P, o);
+        if (WANT & PNBX_WANT_ACC) {
+            Ax += __shfl_xor_sync(FULL, Ax, o);
+            Ay += __shfl_xor_sync(FULL, Ay, o);
+            Az += __shfl_xor_sync(FULL, Az, o);
+        }
+    }
+    if (lane == 0) {
+        double* op = a.out_pot;
+        double* oa = a.out_acc;
+        if (a.slices.n > 0) {
+            const int64_t gi = a.self ? (int64_t)a.perm[skip] : oslot;
+            int o = 0;
+            while (o + 1 < a.slices.n && gi >= a.slices.bounds[o + 1]) ++o;
+            oslot = gi - a.slices.bounds[o];
+            op = a.slices.pot[o];
+            oa = a.slices.acc[o];
+        }
+        if (WANT & PNBX_WANT_POT) op[oslot] = P;
+        if (WANT & PNBX_WANT_ACC) { oa[3 * oslot] = Ax; oa[3 * oslot + 1] = Ay; oa[3 * oslot + 2] = Az; }
+    }
+}
+
+template <int SMODE>
+void launch_walk_wpt(int order, int want, const WalkArgs<float>& a, cudaStream_t s) {
+    const unsigned grid = (unsigned)std::max<int64_t>(1, ceil_div(a.m * 32, WT));
+#define PNBX_W(O, W)                                                        \
+    if (order == O && want == W) {                                          \
+        PNBX_LAUNCH((walk_wpt_kernel<O, W, SMODE>), grid, WT, 0, s, a);     \
+        return;                                                             \
+    }
+    PNBX_W(1, 1) PNBX_W(1, 2) PNBX_W(1, 3)
+    PNBX_W(2, 1) PNBX_W(2, 2) PNBX_W(2, 3)
+    PNBX_W(3, 1) PNBX_W(3, 2) PNBX_W(3, 3)
+    PNBX_W(4, 1) PNBX_W(4, 2) PNBX_W(4, 3)
+    PNBX_W(5, 1) PNBX_W(5, 2) PNBX_W(5, 3)
+#undef PNBX_W
+    throw ArgError{PNBX_ERR_ARG, "internal: no walk kernel variant"};
+}
+
 __global__ void point_keys(const double* __restrict__ pos, int64_t n, const double* __restrict__ root4,
                            uint64_t* __restrict__ key) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -461,6 +635,8 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
     // device walks its block-cyclic share of that order (balanced whatever the layout of the caller's array)
     const bool pts_cyclic = !self && ex.block_cyclic;
     const int64_t m_walk = pts_cyclic ? pnbx_shard_count(m, ex.shard_block, ex.shard_world, ex.shard_rank) : m;
+    // size of the whole call this walk is a share of (multi-device: every device sees the same number)
+    const int64_t wpt_basis = (ex.block_cyclic && self) ? t.n : m;
     DevBuf<uint32_t> tlist, torder;
     tm.begin("octree.walk.prepare_targets");
     const bool tree_order = self && ex.tree_order;
@@ -535,7 +711,16 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         fill(a);
         a.moments = t.moments32.p; a.K = t.rec32; a.src = t.src32.p; a.src_h = t.has_h ? t.sh32.p : zero_h.p;
         const bool any_soft = t.has_h || t.has_hmax;
-        if (!any_soft) launch_walk<float, 0>(order, want, a, s);
+        // few targets: one warp per target (the choice depends on the size of the WHOLE call, `wpt_basis`, so that a
+        // multi-device share runs the kernel the single-device call would run: bit-identical results)
+        const char* wpt_env = getenv("PNBX_WPT_MAX_TARGETS");
+        const int64_t wpt_max = wpt_env ? atoll(wpt_env) : (int64_t)98304;
+        const bool wpt = wpt_basis <= wpt_max;
+        if (wpt) {
+            if (!any_soft) launch_walk_wpt<0>(order, want, a, s);
+            else if (t.kernel == PNBX_KERNEL_SPLINE) launch_walk_wpt<2>(order, want, a, s);
+            else launch_walk_wpt<1>(order, want, a, s);
+        } else if (!any_soft) launch_walk<float, 0>(order, want, a, s);
         else if (t.kernel == PNBX_KERNEL_SPLINE) launch_walk<float, 2>(order, want, a, s);
         else launch_walk<float, 1>(order, want, a, s);
     }
