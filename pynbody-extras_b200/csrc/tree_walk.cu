@@ -22,7 +22,9 @@ namespace {
 #define PNBX_WT 128
 #endif
 #ifndef PNBX_WALK_MINB
-#define PNBX_WALK_MINB 12  // 40 registers: 48 of 64 warps resident (measured best for potentials, profiles/)
+#define PNBX_WALK_MINB 10  // 48 registers: 40 of 64 warps resident. With the record loads issued together (load_rec) this
+                           // beats 12 blocks / 40 registers (which then spills) and 8 / 63: 38.7 / 38.2 ms vs 42.1 / 38.9 and
+                           // 40.3 / 40.8 (potentials / accelerations, N = 1e7, profiles/r02_walk_kernel_ncu.md)
 #endif
 constexpr int WT = PNBX_WT;  // threads per block (independent warps)
 #ifndef PNBX_LEAF_UNROLL
@@ -65,6 +67,31 @@ struct WalkArgs {
     double* out_acc;
     OutSlices slices;         // multi-device self evaluation: results go to the owner of the ORIGINAL index (peer stores)
 };
+
+// One node record = four 16-byte loads issued TOGETHER at the top of a visit. Left to the compiler, the loads of the
+// fields a visit needs later (the COM for the opening test) were sunk below the `kind` dispatch and the warp paid two
+// dependent memory latencies per visit (ncu source page: 10 % + 12 % of the stall samples on the two first uses).
+__device__ __forceinline__ NodeRec load_rec(const NodeRec* __restrict__ p) {
+    uint4 q0, q1, q2, q3;
+    const uint4* r = reinterpret_cast<const uint4*>(p);
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "l"(r));
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(r + 1));
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q2.x), "=r"(q2.y), "=r"(q2.z), "=r"(q2.w) : "l"(r + 2));
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q3.x), "=r"(q3.y), "=r"(q3.z), "=r"(q3.w) : "l"(r + 3));
+    NodeRec c;
+    c.com[0] = __hiloint2double((int)q0.y, (int)q0.x);
+    c.com[1] = __hiloint2double((int)q0.w, (int)q0.z);
+    c.com[2] = __hiloint2double((int)q1.y, (int)q1.x);
+    c.size2 = __hiloint2double((int)q1.w, (int)q1.z);
+    c.gate2 = __hiloint2double((int)q2.y, (int)q2.x);
+    c.next_branch = (int)q2.z;
+    c.first = (int)q2.w;
+    c.kind = (int)q3.x;
+    c.nleaf = (int)q3.y;
+    c.ref = (int)q3.z;
+    c.pad_ = 0;
+    return c;
+}
 
 template <class T>
 __device__ __forceinline__ T tiny_v();
@@ -222,7 +249,7 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
     int resume = INT_MIN;
     int idx = __ballot_sync(FULL, valid) ? 0 : -1;
     while (idx >= 0) {
-        const NodeRec c = a.rec[idx];  // one 64-byte record: one memory round trip per visit
+        const NodeRec c = load_rec(a.rec + idx);  // one 64-byte record: one memory round trip per visit
         const NodeRec& gm = c;
         if (!active && resume == idx) active = true;
         if (WANT == 0) {  // a leaf-run record stands for `nleaf` reference nodes (tree.cuh)
