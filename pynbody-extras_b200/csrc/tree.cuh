@@ -109,7 +109,8 @@ struct pnbx_tree_impl {
 void tree_init(pnbx_tree_impl& t, int device, int64_t n, int64_t leaf_capacity, int multipole_order, int kernel,
                bool has_mass, bool has_h);
 void tree_build(pnbx_tree_impl& t, StageTimer& tm);
-void tree_build_mass(pnbx_tree_impl& t, StageTimer& tm);              // build_mass (tree.rs:968-1012) on t.stream
+void tree_build_mass(pnbx_tree_impl& t, StageTimer& tm, bool regather);  // build_mass (tree.rs:968-1012) on t.stream;
+                                                                         // regather: masses were replaced
 void tree_mark_ready(pnbx_tree_impl& t);                              // record `ready` on t.stream
 void tree_begin_use(const pnbx_tree_impl& t, cudaStream_t s);         // s waits for the tree to be ready
 void tree_end_use(const pnbx_tree_impl& t, cudaStream_t s);           // t.stream waits for the work queued on s

@@ -35,11 +35,15 @@ __global__ void root_from_bbox(const double* __restrict__ bb, double* __restrict
 // ------------------------------------------------------------------------------------------ K3
 // Octant digits of levels 1..42 by the reference's descent: oct = (x>=cx) | (y>=cy)<<1 | (z>=cz)<<2
 // against the *rounded* child centres centre +/- half/2 (tree.rs:818-838).
-__global__ void path_keys(const double* __restrict__ pos, int64_t n, const double* __restrict__ root4, int levels,
-                          uint64_t* __restrict__ key_hi, uint64_t* __restrict__ key_lo) {
+// `packed` (nullable): (x, y, z, m) as one 32-byte record per particle, written here because the positions are in
+// registers anyway; the gather into tree order then fetches ONE sector per particle instead of two or three.
+__global__ void path_keys(const double* __restrict__ pos, const double* __restrict__ mass, int64_t n,
+                          const double* __restrict__ root4, int levels, uint64_t* __restrict__ key_hi,
+                          uint64_t* __restrict__ key_lo, double4* __restrict__ packed) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+    if (packed) packed[i] = make_double4(x, y, z, mass ? mass[i] : 1.0);
     double cx = root4[0], cy = root4[1], cz = root4[2], hf = root4[3];
     uint64_t hi = 0, lo = 0;
     for (int l = 1; l <= levels; ++l) {
@@ -346,6 +350,14 @@ __global__ void gather_sources(const double* __restrict__ pos, const double* __r
     spos[3 * s] = x; spos[3 * s + 1] = y; spos[3 * s + 2] = z;
     if (smass) smass[s] = mass[i];
 }
+__global__ void gather_packed_sources(const double4* __restrict__ packed, const uint32_t* __restrict__ perm, int64_t n,
+                                      double* __restrict__ spos, double* __restrict__ smass) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const double4 v = packed[perm[s]];
+    spos[3 * s] = v.x; spos[3 * s + 1] = v.y; spos[3 * s + 2] = v.z;
+    if (smass) smass[s] = v.w;
+}
 __global__ void gather_soft(const double* __restrict__ h, const uint32_t* __restrict__ perm, int64_t n,
                             double* __restrict__ sh, float* __restrict__ sh32) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,6 +369,73 @@ __global__ void gather_soft(const double* __restrict__ h, const uint32_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------ K6
+// fp32 walk records from the float64 moments (layout: multipole.cuh, m2p_fast). Called by the payload kernels right
+// after a node's moments are final, so the float64 moments are not read again by a separate packing pass.
+__device__ __forceinline__ void pack_walk_record(const double* __restrict__ m, int order, float* __restrict__ o) {
+    using namespace mp;
+    if (order <= 1) { o[0] = (float)m[I000]; return; }
+    o[0] = (float)m[I000];
+    if (order <= 3) {  // m2p_fast layout: traceless T = 3 (S - trS/3 I), folded cubic C' = 15 C - 3 (w.u)(u.u)
+        const double tr = m[I200] + m[I020] + m[I002];
+        o[1] = (float)(3.0 * m[I200] - tr); o[2] = (float)(3.0 * m[I020] - tr); o[3] = (float)(3.0 * m[I002] - tr);
+        o[4] = (float)(1.5 * m[I110]); o[5] = (float)(1.5 * m[I101]); o[6] = (float)(1.5 * m[I011]);
+        o[7] = 0.f;
+        if (order == 3) {
+            const double wx = 3.0 * m[I300] + m[I120] + m[I102];
+            const double wy = 3.0 * m[I030] + m[I210] + m[I012];
+            const double wz = 3.0 * m[I003] + m[I201] + m[I021];
+            // field order: 300 030 003 210 201 120 102 021 012 111; the w component is that of the odd-power axis
+            o[8]  = (float)(15.0 * m[I300] - 3.0 * wx); o[9]  = (float)(15.0 * m[I030] - 3.0 * wy);
+            o[10] = (float)(15.0 * m[I003] - 3.0 * wz); o[11] = (float)(15.0 * m[I210] - 3.0 * wy);
+            o[12] = (float)(15.0 * m[I201] - 3.0 * wz); o[13] = (float)(15.0 * m[I120] - 3.0 * wx);
+            o[14] = (float)(15.0 * m[I102] - 3.0 * wx); o[15] = (float)(15.0 * m[I021] - 3.0 * wz);
+            o[16] = (float)(15.0 * m[I012] - 3.0 * wy); o[17] = (float)(15.0 * m[I111]);
+            o[18] = o[19] = 0.f;
+        }
+        return;
+    }
+    // orders 4, 5 (m2p_fast45): [1..6] 6S, [7] 3 trS, [8..17] octupole, [18..20] 9 v = 3 w
+    o[1] = (float)(6.0 * m[I200]); o[2] = (float)(6.0 * m[I020]); o[3] = (float)(6.0 * m[I002]);
+    o[4] = (float)(3.0 * m[I110]); o[5] = (float)(3.0 * m[I101]); o[6] = (float)(3.0 * m[I011]);
+    o[7] = (float)(3.0 * (m[I200] + m[I020] + m[I002]));
+    for (int t = 0; t < 10; ++t) o[8 + t] = (float)m[I300 + t];
+    o[18] = (float)(3.0 * (3.0 * m[I300] + m[I120] + m[I102]));
+    o[19] = (float)(3.0 * (3.0 * m[I030] + m[I210] + m[I012]));
+    o[20] = (float)(3.0 * (3.0 * m[I003] + m[I201] + m[I021]));
+    o[21] = o[22] = o[23] = 0.f;
+    if (order >= 4) {
+        for (int t = 0; t < 15; ++t) o[24 + t] = (float)m[I400 + t];
+        o[39] = (float)(12.0 * m[I400] + 2.0 * m[I220] + 2.0 * m[I202]);
+        o[40] = (float)(12.0 * m[I040] + 2.0 * m[I220] + 2.0 * m[I022]);
+        o[41] = (float)(12.0 * m[I004] + 2.0 * m[I202] + 2.0 * m[I022]);
+        o[42] = (float)(6.0 * m[I310] + 6.0 * m[I130] + 2.0 * m[I112]);
+        o[43] = (float)(6.0 * m[I301] + 6.0 * m[I103] + 2.0 * m[I121]);
+        o[44] = (float)(6.0 * m[I031] + 6.0 * m[I013] + 2.0 * m[I211]);
+        o[45] = (float)(24.0 * (m[I400] + m[I040] + m[I004]) + 8.0 * (m[I220] + m[I202] + m[I022]));
+        o[46] = o[47] = 0.f;
+    }
+    if (order >= 5) {
+        for (int t = 0; t < 21; ++t) o[48 + t] = (float)m[I500 + t];
+        const double x3 = 20.0 * m[I500] + 2.0 * m[I320] + 2.0 * m[I302];
+        const double y3 = 20.0 * m[I050] + 2.0 * m[I230] + 2.0 * m[I032];
+        const double z3 = 20.0 * m[I005] + 2.0 * m[I203] + 2.0 * m[I023];
+        const double x2y = 12.0 * m[I410] + 6.0 * m[I230] + 2.0 * m[I212];
+        const double x2z = 12.0 * m[I401] + 6.0 * m[I203] + 2.0 * m[I221];
+        const double xy2 = 12.0 * m[I140] + 6.0 * m[I320] + 2.0 * m[I122];
+        const double xz2 = 12.0 * m[I104] + 6.0 * m[I302] + 2.0 * m[I122];
+        const double y2z = 12.0 * m[I041] + 6.0 * m[I023] + 2.0 * m[I221];
+        const double yz2 = 12.0 * m[I014] + 6.0 * m[I032] + 2.0 * m[I212];
+        const double xyz = 6.0 * (m[I311] + m[I131] + m[I113]);
+        o[69] = (float)x3; o[70] = (float)y3; o[71] = (float)z3; o[72] = (float)x2y; o[73] = (float)x2z;
+        o[74] = (float)xy2; o[75] = (float)xz2; o[76] = (float)y2z; o[77] = (float)yz2; o[78] = (float)xyz;
+        o[79] = (float)(6.0 * x3 + 2.0 * xy2 + 2.0 * xz2);
+        o[80] = (float)(6.0 * y3 + 2.0 * x2y + 2.0 * yz2);
+        o[81] = (float)(6.0 * z3 + 2.0 * x2z + 2.0 * y2z);
+        o[82] = o[83] = 0.f;
+    }
+}
+
+
 // One thread per node of one level (deepest level first). Children are contiguous reference ids in
 // octant order, so the sums run in the reference's order (tree.rs:876-929, 945-962, 1023-1063).
 struct PayloadArgs {
@@ -364,6 +443,7 @@ struct PayloadArgs {
     const uint32_t* start; const uint32_t* pcount; const uint8_t* nchild; const int32_t* first_subnode;
     const double* spos; const double* smass; const double* sh;
     double* nmass; double* ncom; double* hmax; double* moments; int order; int ncoef;
+    const int32_t* dfs; float* moments32; int rec32;  // fp32 walk records, written in depth-first order
 };
 // Leaves: one launch over ALL nodes (P2M has no dependencies), one thread per node, internal nodes return at once.
 // Mass / COM / hmax in leaf-list order (tree.rs:881-905, 947-952), then P2M about the COM (tree.rs:1030-1042).
@@ -410,6 +490,7 @@ __global__ void __launch_bounds__(128) payload_leaves(PayloadArgs a) {
     }
 #pragma unroll
     for (int t = 0; t < NC; ++t) a.moments[id * NC + t] = mom[t];
+    pack_walk_record(mom, a.order, a.moments32 + (int64_t)a.dfs[id] * a.rec32);
 }
 
 // Internal nodes of one level, 8 lanes per node (lane l <-> child slot l): every lane loads its child's mass / COM /
@@ -486,6 +567,13 @@ __global__ void __launch_bounds__(mp::stored_coeffs(ORDER) > 35 ? 64 : 128) payl
                     if (nzmask & (1u << k)) acc = __dadd_rn(acc, s_tr[g][k][t]);
             a.moments[(int64_t)id * NC + t] = acc;
         }
+    }
+    __syncwarp();  // the group's coefficient stores are visible to its lane 0
+    if (node_ok && lane8 == 0) {
+        double mom[NC];
+#pragma unroll
+        for (int t = 0; t < NC; ++t) mom[t] = a.moments[(int64_t)id * NC + t];
+        pack_walk_record(mom, a.order, a.moments32 + (int64_t)a.dfs[id] * a.rec32);
     }
 }
 
@@ -569,76 +657,6 @@ __global__ void update_gates(const double* __restrict__ hmax, double csep, const
     const double ch = __dmul_rn(csep, fmax(hmax[i], 0.0));
     rec[dfs[i]].gate2 = __dmul_rn(ch, ch);
 }
-// fp32 walk records from the float64 moments (layout: multipole.cuh, m2p_fast)
-__global__ void pack_walk_moments(const double* __restrict__ mom, const int32_t* __restrict__ dfs, int64_t nn, int order,
-                                  int K, int rec, float* __restrict__ out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nn) return;
-    const double* m = mom + i * K;
-    float* o = out + (int64_t)dfs[i] * rec;  // fp32 records follow the walk records' depth-first order
-    using namespace mp;
-    if (order <= 1) { o[0] = (float)m[I000]; return; }
-    o[0] = (float)m[I000];
-    if (order <= 3) {  // m2p_fast layout: traceless T = 3 (S - trS/3 I), folded cubic C' = 15 C - 3 (w.u)(u.u)
-        const double tr = m[I200] + m[I020] + m[I002];
-        o[1] = (float)(3.0 * m[I200] - tr); o[2] = (float)(3.0 * m[I020] - tr); o[3] = (float)(3.0 * m[I002] - tr);
-        o[4] = (float)(1.5 * m[I110]); o[5] = (float)(1.5 * m[I101]); o[6] = (float)(1.5 * m[I011]);
-        o[7] = 0.f;
-        if (order == 3) {
-            const double wx = 3.0 * m[I300] + m[I120] + m[I102];
-            const double wy = 3.0 * m[I030] + m[I210] + m[I012];
-            const double wz = 3.0 * m[I003] + m[I201] + m[I021];
-            // field order: 300 030 003 210 201 120 102 021 012 111; the w component is that of the odd-power axis
-            o[8]  = (float)(15.0 * m[I300] - 3.0 * wx); o[9]  = (float)(15.0 * m[I030] - 3.0 * wy);
-            o[10] = (float)(15.0 * m[I003] - 3.0 * wz); o[11] = (float)(15.0 * m[I210] - 3.0 * wy);
-            o[12] = (float)(15.0 * m[I201] - 3.0 * wz); o[13] = (float)(15.0 * m[I120] - 3.0 * wx);
-            o[14] = (float)(15.0 * m[I102] - 3.0 * wx); o[15] = (float)(15.0 * m[I021] - 3.0 * wz);
-            o[16] = (float)(15.0 * m[I012] - 3.0 * wy); o[17] = (float)(15.0 * m[I111]);
-            o[18] = o[19] = 0.f;
-        }
-        return;
-    }
-    // orders 4, 5 (m2p_fast45): [1..6] 6S, [7] 3 trS, [8..17] octupole, [18..20] 9 v = 3 w
-    o[1] = (float)(6.0 * m[I200]); o[2] = (float)(6.0 * m[I020]); o[3] = (float)(6.0 * m[I002]);
-    o[4] = (float)(3.0 * m[I110]); o[5] = (float)(3.0 * m[I101]); o[6] = (float)(3.0 * m[I011]);
-    o[7] = (float)(3.0 * (m[I200] + m[I020] + m[I002]));
-    for (int t = 0; t < 10; ++t) o[8 + t] = (float)m[I300 + t];
-    o[18] = (float)(3.0 * (3.0 * m[I300] + m[I120] + m[I102]));
-    o[19] = (float)(3.0 * (3.0 * m[I030] + m[I210] + m[I012]));
-    o[20] = (float)(3.0 * (3.0 * m[I003] + m[I201] + m[I021]));
-    o[21] = o[22] = o[23] = 0.f;
-    if (order >= 4) {
-        for (int t = 0; t < 15; ++t) o[24 + t] = (float)m[I400 + t];
-        o[39] = (float)(12.0 * m[I400] + 2.0 * m[I220] + 2.0 * m[I202]);
-        o[40] = (float)(12.0 * m[I040] + 2.0 * m[I220] + 2.0 * m[I022]);
-        o[41] = (float)(12.0 * m[I004] + 2.0 * m[I202] + 2.0 * m[I022]);
-        o[42] = (float)(6.0 * m[I310] + 6.0 * m[I130] + 2.0 * m[I112]);
-        o[43] = (float)(6.0 * m[I301] + 6.0 * m[I103] + 2.0 * m[I121]);
-        o[44] = (float)(6.0 * m[I031] + 6.0 * m[I013] + 2.0 * m[I211]);
-        o[45] = (float)(24.0 * (m[I400] + m[I040] + m[I004]) + 8.0 * (m[I220] + m[I202] + m[I022]));
-        o[46] = o[47] = 0.f;
-    }
-    if (order >= 5) {
-        for (int t = 0; t < 21; ++t) o[48 + t] = (float)m[I500 + t];
-        const double x3 = 20.0 * m[I500] + 2.0 * m[I320] + 2.0 * m[I302];
-        const double y3 = 20.0 * m[I050] + 2.0 * m[I230] + 2.0 * m[I032];
-        const double z3 = 20.0 * m[I005] + 2.0 * m[I203] + 2.0 * m[I023];
-        const double x2y = 12.0 * m[I410] + 6.0 * m[I230] + 2.0 * m[I212];
-        const double x2z = 12.0 * m[I401] + 6.0 * m[I203] + 2.0 * m[I221];
-        const double xy2 = 12.0 * m[I140] + 6.0 * m[I320] + 2.0 * m[I122];
-        const double xz2 = 12.0 * m[I104] + 6.0 * m[I302] + 2.0 * m[I122];
-        const double y2z = 12.0 * m[I041] + 6.0 * m[I023] + 2.0 * m[I221];
-        const double yz2 = 12.0 * m[I014] + 6.0 * m[I032] + 2.0 * m[I212];
-        const double xyz = 6.0 * (m[I311] + m[I131] + m[I113]);
-        o[69] = (float)x3; o[70] = (float)y3; o[71] = (float)z3; o[72] = (float)x2y; o[73] = (float)x2z;
-        o[74] = (float)xy2; o[75] = (float)xz2; o[76] = (float)y2z; o[77] = (float)yz2; o[78] = (float)xyz;
-        o[79] = (float)(6.0 * x3 + 2.0 * xy2 + 2.0 * xz2);
-        o[80] = (float)(6.0 * y3 + 2.0 * x2y + 2.0 * yz2);
-        o[81] = (float)(6.0 * z3 + 2.0 * x2z + 2.0 * y2z);
-        o[82] = o[83] = 0.f;
-    }
-}
-
 inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)std::max<int64_t>(1, ceil_div(n, t)); }
 
 int bits_for(uint64_t v) {
@@ -894,11 +912,11 @@ void tree_init(pnbx_tree_impl& t, int device, int64_t n, int64_t leaf_capacity, 
 }
 
 // tree.rs:968-1012
-void tree_build_mass(pnbx_tree_impl& t, StageTimer& tm) {
+void tree_build_mass(pnbx_tree_impl& t, StageTimer& tm, bool regather) {
     cudaStream_t s = t.stream;
     const int64_t nn = t.nn;
     tm.begin("octree.payload.alloc_gather");
-    gather_sorted_sources(t, s);  // masses may have been replaced
+    if (regather) gather_sorted_sources(t, s);  // build_mass(): masses may have been replaced
     t.has_hmax = t.has_h;
     t.n_moments = mp::stored_coeffs(t.order);
     t.rec32 = mp::fast_rec_floats(t.order);
@@ -917,6 +935,7 @@ void tree_build_mass(pnbx_tree_impl& t, StageTimer& tm) {
     a.spos = t.spos.p; a.smass = t.has_mass ? t.smass.p : nullptr; a.sh = t.has_h ? t.sh.p : nullptr;
     a.nmass = t.nmass.p; a.ncom = t.ncom.p; a.hmax = t.has_hmax ? t.hmax.p : nullptr; a.moments = t.moments.p;
     a.order = t.order; a.ncoef = t.n_moments;
+    a.dfs = t.dfs_of_ref.p; a.moments32 = t.moments32.p; a.rec32 = t.rec32;
     const int eff = t.order <= 1 ? 0 : t.order;
     auto launch = [&](bool leaves) {
 #define PNBX_P(O)                                                                                            \
@@ -948,8 +967,6 @@ void tree_build_mass(pnbx_tree_impl& t, StageTimer& tm) {
     PNBX_LAUNCH(merge_leaf_runs, nblk(nn), 256, 0, s, t.node_nchild.p, t.first_subnode.p, t.node_start.p, t.node_count.p,
                 t.next_branch.p, t.nmass.p, t.ncom.p, t.spos.p, t.has_mass ? t.smass.p : nullptr, t.dfs_of_ref.p, nn,
                 t.rec.p, t.n > 0 ? t.src32.p : nullptr);
-    PNBX_LAUNCH(pack_walk_moments, nblk(nn), 256, 0, s, t.moments.p, t.dfs_of_ref.p, nn, t.order, t.n_moments, t.rec32,
-                t.moments32.p);
     PNBX_CUDA(cudaGetLastError());
     t.has_payload = true;
     tm.end();
@@ -980,6 +997,7 @@ void tree_build(pnbx_tree_impl& t, StageTimer& tm) {
         uint32_t *iota = nullptr, *idx1 = nullptr;
         uint64_t *tmpk = nullptr, *hi1 = nullptr;
         uint8_t* sort_tmp = nullptr;
+        double4* packed = nullptr;
         size_t sort_bytes = 0;
         if (n > 0)
             PNBX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k.skhi, k.skhi, iota, iota, (int)n, 0, 63, s));
@@ -990,6 +1008,7 @@ void tree_build(pnbx_tree_impl& t, StageTimer& tm) {
             sort_tmp = S1.take<uint8_t>(sort_bytes);
             k.bq = S1.take<int8_t>(m); k.Dq = S1.take<int8_t>(m);
             k.nodes_here = S1.take<int32_t>(m); k.base = S1.take<int32_t>(m + 1);
+            packed = S1.take<double4>(m);
             if (two) {
                 k.sklo = S1.take<uint64_t>(m); tmpk = S1.take<uint64_t>(m); hi1 = S1.take<uint64_t>(m);
                 idx1 = S1.take<uint32_t>(m);
@@ -998,7 +1017,8 @@ void tree_build(pnbx_tree_impl& t, StageTimer& tm) {
         }
         if (n > 0) {
             tm.begin("octree.keys_sort");
-            PNBX_LAUNCH(path_keys, nblk(n), 256, 0, s, t.pos.p, n, t.root4.p, levels, t.key_hi.p, two ? t.key_lo.p : nullptr);
+            PNBX_LAUNCH(path_keys, nblk(n), 256, 0, s, t.pos.p, t.has_mass ? t.mass.p : nullptr, n, t.root4.p, levels,
+                        t.key_hi.p, two ? t.key_lo.p : nullptr, packed);
             PNBX_LAUNCH(iota_u32, nblk(n), 256, 0, s, iota, n);
             auto sort63 = [&](const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout) {
                 size_t bytes = sort_bytes;
@@ -1016,14 +1036,16 @@ void tree_build(pnbx_tree_impl& t, StageTimer& tm) {
             tm.end();
         }
         ok = build_topology(t, s, k, levels, tm);
+        if (ok && n > 0)  // sorted float64 copies, from the packed records while the scratch slab is alive
+            PNBX_LAUNCH(gather_packed_sources, nblk(n), 256, 0, s, packed, t.perm.p, n, t.spos.p,
+                        t.has_mass ? t.smass.p : nullptr);
     }
     if (!ok)
         throw ArgError{PNBX_ERR_DEPTH,
                        "octree deeper than 42 levels (more than leaf_capacity coincident or nearly coincident "
                        "points); the reference would recurse without bound here"};
     gather_sorted_soft(t, s);
-    if (t.has_mass) tree_build_mass(t, tm);  // gravity.rs:210-220
-    else gather_sorted_sources(t, s);
+    if (t.has_mass) tree_build_mass(t, tm, false);  // gravity.rs:210-220
 }
 
 }  // namespace pnbx
@@ -1109,7 +1131,7 @@ extern "C" int pnbx_tree_build_mass_ex(pnbx_tree* tp, const double* mass, const 
                 Exec ex = make_exec_for(r.device, r.stream);
                 StageTimer tm(r.stream);
                 if (mass) { copy_into_tree(r, ex, r.mass.p, mass, (size_t)r.n); r.has_mass = true; }
-                tree_build_mass(r, tm);
+                tree_build_mass(r, tm, true);
                 tree_mark_ready(r);
                 PNBX_CUDA(cudaStreamSynchronize(r.stream));
             });
@@ -1123,7 +1145,7 @@ extern "C" int pnbx_tree_build_mass_ex(pnbx_tree* tp, const double* mass, const 
             copy_into_tree(t, ex, t.mass.p, mass, (size_t)t.n);
             t.has_mass = true;
         }
-        tree_build_mass(t, tm);
+        tree_build_mass(t, tm, true);
         tree_publish(t, ex);
     });
 }
