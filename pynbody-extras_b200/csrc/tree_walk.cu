@@ -662,8 +662,10 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
     // device walks its block-cyclic share of that order (balanced whatever the layout of the caller's array)
     const bool pts_cyclic = !self && ex.block_cyclic;
     const int64_t m_walk = pts_cyclic ? pnbx_shard_count(m, ex.shard_block, ex.shard_world, ex.shard_rank) : m;
-    // size of the whole call this walk is a share of (multi-device: every device sees the same number)
-    const int64_t wpt_basis = (ex.block_cyclic && self) ? t.n : m;
+    // kernel choice: self evaluations go by the size of the WHOLE call (a multi-device share then runs the kernel the
+    // single-device call would run: bit-identical results); query points go by what THIS device walks — a grid spread
+    // over 8 GPUs is 8 small, heavy-tailed calls, which is exactly what the warp-per-target kernel is for
+    const int64_t wpt_basis = self ? (ex.block_cyclic ? t.n : m) : m_walk;
     DevBuf<uint32_t> tlist, torder;
     tm.begin("octree.walk.prepare_targets");
     const bool tree_order = self && ex.tree_order;
@@ -738,10 +740,9 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         fill(a);
         a.moments = t.moments32.p; a.K = t.rec32; a.src = t.src32.p; a.src_h = t.has_h ? t.sh32.p : zero_h.p;
         const bool any_soft = t.has_h || t.has_hmax;
-        // few targets: one warp per target (the choice depends on the size of the WHOLE call, `wpt_basis`, so that a
-        // multi-device share runs the kernel the single-device call would run: bit-identical results)
+        // few targets: one warp per target
         const char* wpt_env = getenv("PNBX_WPT_MAX_TARGETS");
-        const int64_t wpt_max = wpt_env ? atoll(wpt_env) : (int64_t)98304;
+        const int64_t wpt_max = wpt_env ? atoll(wpt_env) : (int64_t)131072;
         const bool wpt = wpt_basis <= wpt_max;
         if (wpt) {
             if (!any_soft) launch_walk_wpt<0>(order, want, a, s);

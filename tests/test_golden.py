@@ -17,6 +17,13 @@ T = np.load(os.path.join(HERE, "golden", "tree_golden.npz"))
 DIRECT = (("newton", None, False), ("plummer", 0, True), ("spline", 1, True))
 
 
+@pytest.fixture(autouse=True, params=["lane", "warp"])
+def walk_kernel_choice(request, monkeypatch):
+    """Every test runs with both fp32 walk kernels: one target per lane (large calls) and one target per warp (calls
+    with few targets; PNBX_WPT_MAX_TARGETS is the switch-over size, default 131072)."""
+    monkeypatch.setenv("PNBX_WPT_MAX_TARGETS", "0" if request.param == "lane" else "4000000000")
+
+
 def rms_rel_vec(a, ref):
     return np.sqrt((((a - ref) ** 2).sum(1) / (ref ** 2).sum(1)).mean())
 
