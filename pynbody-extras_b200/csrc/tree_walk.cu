@@ -741,8 +741,12 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         a.moments = t.moments32.p; a.K = t.rec32; a.src = t.src32.p; a.src_h = t.has_h ? t.sh32.p : zero_h.p;
         const bool any_soft = t.has_h || t.has_hmax;
         // few targets: one warp per target
+        // switch-over sizes: the warp-per-target kernel costs ~40 warp instructions per visit and target, the
+        // lane-per-target kernel's time on small calls is set by its heaviest warps. Query grids are heavy-tailed (points
+        // in a softened core sum thousands of particles), so they switch later (N = 1e8 zoom set, 2.5e5 grid points per
+        // GPU: 129 ms lane-per-target; 1.25e5 per GPU: 128 ms vs 14 ms warp-per-target)
         const char* wpt_env = getenv("PNBX_WPT_MAX_TARGETS");
-        const int64_t wpt_max = wpt_env ? atoll(wpt_env) : (int64_t)131072;
+        const int64_t wpt_max = wpt_env ? atoll(wpt_env) : (int64_t)(self ? 131072 : 262144);
         const bool wpt = wpt_basis <= wpt_max;
         if (wpt) {
             if (!any_soft) launch_walk_wpt<0>(order, want, a, s);

@@ -66,7 +66,9 @@ def assert_same_payload(g, o):
 
 
 @pytest.mark.parametrize("n,cap,order", [(1, 8, 3), (7, 8, 0), (9, 8, 3), (300, 1, 2), (5000, 8, 3), (5000, 32, 5),
-                                         (20000, 8, 4), (3000, 128, 1)])
+                                         (20000, 8, 4), (3000, 128, 1),
+                                         # leaf capacities > 32: sliding-window maximum (van Herk) + global leaf ordering
+                                         (1000, 33, 3), (50000, 200, 2), (4097, 4096, 0), (2000, 2000, 3), (6000, 1000, 2)])
 def test_topology_and_payload_bit_exact(n, cap, order):
     pos, m = plummer(n, seed=100 + n)
     g = R().Octree(pos, m, cap, order)
