@@ -741,12 +741,14 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         a.moments = t.moments32.p; a.K = t.rec32; a.src = t.src32.p; a.src_h = t.has_h ? t.sh32.p : zero_h.p;
         const bool any_soft = t.has_h || t.has_hmax;
         // few targets: one warp per target
-        // switch-over sizes: the warp-per-target kernel costs ~40 warp instructions per visit and target, the
-        // lane-per-target kernel's time on small calls is set by its heaviest warps. Query grids are heavy-tailed (points
-        // in a softened core sum thousands of particles), so they switch later (N = 1e8 zoom set, 2.5e5 grid points per
-        // GPU: 129 ms lane-per-target; 1.25e5 per GPU: 128 ms vs 14 ms warp-per-target)
+        // switch-over sizes (measured, profiles/r02_walk_kernel_ncu.md): the warp-per-target kernel costs ~40 warp
+        // instructions per visit and target, so for the balanced self evaluations it only wins on very small sets
+        // (N = 15 682: 0.61 vs 0.72 ms; N = 60 000: 2.8 vs 0.87 ms). The lane-per-target kernel's time on a query grid is
+        // set by its heaviest warps (points in a softened core sum thousands of particles): grids switch much later
+        // (N = 1e7 zoom set: 1.25e5 points 6.6 vs 8.1 ms, 2e5 points 10.4 vs 7.2 ms; N = 1e8 on 8 GPUs, 1.25e5 points
+        // per GPU: 14 vs 128 ms)
         const char* wpt_env = getenv("PNBX_WPT_MAX_TARGETS");
-        const int64_t wpt_max = wpt_env ? atoll(wpt_env) : (int64_t)(self ? 131072 : 262144);
+        const int64_t wpt_max = wpt_env ? atoll(wpt_env) : (int64_t)(self ? 16384 : 131072);
         const bool wpt = wpt_basis <= wpt_max;
         if (wpt) {
             if (!any_soft) launch_walk_wpt<0>(order, want, a, s);

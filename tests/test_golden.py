@@ -20,7 +20,7 @@ DIRECT = (("newton", None, False), ("plummer", 0, True), ("spline", 1, True))
 @pytest.fixture(autouse=True, params=["lane", "warp"])
 def walk_kernel_choice(request, monkeypatch):
     """Every test runs with both fp32 walk kernels: one target per lane (large calls) and one target per warp (calls
-    with few targets; PNBX_WPT_MAX_TARGETS is the switch-over size, default 131072)."""
+    with few targets; PNBX_WPT_MAX_TARGETS is the switch-over size, default 16384 particles / 131072 query points)."""
     monkeypatch.setenv("PNBX_WPT_MAX_TARGETS", "0" if request.param == "lane" else "4000000000")
 
 

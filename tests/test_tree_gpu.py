@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(autouse=True, params=["lane", "warp"])
 def walk_kernel_choice(request, monkeypatch):
     """Every test runs with both fp32 walk kernels: one target per lane (large calls) and one target per warp (calls
-    with few targets; PNBX_WPT_MAX_TARGETS is the switch-over size, default 131072)."""
+    with few targets; PNBX_WPT_MAX_TARGETS is the switch-over size, default 16384 particles / 131072 query points)."""
     monkeypatch.setenv("PNBX_WPT_MAX_TARGETS", "0" if request.param == "lane" else "4000000000")
 
 TOL32 = 1e-5
