@@ -1,6 +1,6 @@
 """BASELINE.json configs[3]/[4]: zoom-shaped dm/gas/star set, N up to 1e8, tree gravity sharded across the GPUs of
-one box. One process per GPU (torchrun); every rank owns 1/world of the snapshot (generated per rank with
-seed 4+rank — statistically the same set, no 1e8-particle host array per rank), uploads it, ONE all-gather
+one box. One process per GPU (torchrun); every rank owns 1/world of the snapshot (its index range of the deterministic
+zoom set, `zoom_range`: the same global set at any world size, no 1e8-particle host array per rank), uploads it, ONE all-gather
 replicates the sources, every rank builds the identical tree and walks its own target shard.
 
   torchrun --nproc-per-node 8 benchmarks/tree_sharded_bench.py --particles 100000000
@@ -33,7 +33,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from benchmarks.synthetic import rz_grid_targets, zoom_families
+    from benchmarks.synthetic import rz_grid_targets, zoom_range
     from pynbodyext.gravity import device as gdev
     from pynbodyext.gravity.sharded import pack_shard, replicate_sources, shard_bounds
 
@@ -49,8 +49,7 @@ def main():
     lo, hi = b[rank], b[rank + 1]
     per = max(b[r + 1] - b[r] for r in range(world))
     t0 = time.perf_counter()
-    pos, mass, h = zoom_families(hi - lo, seed=4 + rank)
-    mass = mass / world  # total mass 1 over all ranks
+    pos, mass, h, _fam = zoom_range(n, lo, hi, seed=4)
     rows_h = torch.from_numpy(pack_shard(pos, mass, h, 0, hi - lo, per)).pin_memory()
     gen_s = time.perf_counter() - t0
 

@@ -450,3 +450,25 @@ def test_leaf_runs_dense_softened_core(cap, kernel):
     p_q, a_q = o.eval(0.7, targets=q)
     p32, a32 = g._eval(q, 0.7, 3)
     assert rms_rel(p32, p_q) < TOL32 and rms_rel_vec(a32, a_q) < TOL32
+
+
+def test_asv_benchmark_classes_of_the_reference_run_and_match_the_oracle():
+    # benchmarks/asv_gravity.py mirrors the reference's ASV classes (bench_gravity.py:74-166); pynbody's test data are
+    # absent here, so it runs on the synthetic stand-in of halo 0 (15 682 particles). Every timed call works, and the
+    # `TimeTreeGravityFull` / `main()` configuration (theta 0.7, softening 0.001, spline, order 3) matches the oracle.
+    import itertools
+    from benchmarks import asv_gravity as B
+    b = B.TimeTreeConstruct()
+    assert len(b.pos) == 15_682
+    for lc, soft, order in itertools.product([8, 128], [None, 0.288], [0, 5]):
+        b.time_construct_tree(lc, soft, order)
+    B.TimeTreeGravityTheta().time_construct_and_tree_potentials(1.0)
+    B.TimeTreeGravityOrder().time_construct_and_tree_potentials(4)
+    full = B.TimeTreeGravityFull()
+    full.time_construct_and_tree_potentials()
+    p = full._construct_and_tree_potentials(theta=0.7, softening=0.001, kernel=1, multipole_order=3)
+    o = O.Tree(full.pos, full.mass, 8, 3, np.full(len(full.mass), 0.001), 1)
+    assert rms_rel(p, o.eval(0.7, want=1)[0]) < TOL32
+    # theta-only case: Gravity(kernel=None, order 0) -> unsoftened monopole tree
+    p0 = B.TimeTreeGravityTheta()._construct_and_tree_potentials(theta=0.7)
+    assert rms_rel(p0, O.Tree(full.pos, full.mass, 8, 0).eval(0.7, want=1)[0]) < TOL32
