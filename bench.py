@@ -682,12 +682,17 @@ def run_ours(args):
     if world == 1 and not args.no_softened:
         d_hv = to_dev(np.random.default_rng(0).uniform(0.005, 0.02, n))
         for name, kern in (("plummer_pair", 0), ("spline", 1)):
-            for _ in range(2):
-                gdev.direct_device(d_pos, d_mass, d_hv, kernel=kern, want=2, kernel_events=True)
-            torch.cuda.synchronize()
-            ms_v = gdev.last_kernel_ms()
-            softened[name] = {"kernel_ms": ms_v, "achieved": FLOP_PER_INTERACTION * n_int / (ms_v * 1e-3) / 1e12,
-                              "frac": FLOP_PER_INTERACTION * n_int / (ms_v * 1e-3) / 1e12 / meas_tf}
+            for general in (False, True):  # the workload has equal masses: also time the general-mass variant
+                if general:
+                    os.environ["PNBX_DIRECT_NO_CONSTM"] = "1"
+                for _ in range(2):
+                    gdev.direct_device(d_pos, d_mass, d_hv, kernel=kern, want=2, kernel_events=True)
+                torch.cuda.synchronize()
+                ms_v = gdev.last_kernel_ms()
+                os.environ.pop("PNBX_DIRECT_NO_CONSTM", None)
+                softened[name + ("_general_mass" if general else "")] = {
+                    "kernel_ms": ms_v, "achieved": FLOP_PER_INTERACTION * n_int / (ms_v * 1e-3) / 1e12,
+                    "frac": FLOP_PER_INTERACTION * n_int / (ms_v * 1e-3) / 1e12 / meas_tf}
         del d_hv
     roofline = {
         "bound": "fp32", "kernel": "direct_kernel_f2<acc, const_mass> (packed FP32x2; the workload has equal masses)",

@@ -44,7 +44,7 @@ enum Soft { SOFT_NEWTON = 0, SOFT_PLUMMER_CONST = 1, SOFT_PLUMMER_PAIR = 2, SOFT
 // Which kernel variant a call needs depends on the DATA (are the softenings / masses constant? is one negative?).
 // That is decided on the device (classify_direct) and every candidate variant is launched with a gate: the ones that
 // were not chosen return at once. No host round trip, so device-pointer calls stay purely stream-ordered.
-enum Variant { V_F2_CONSTM = 0, V_F2 = 1, V_F2H = 2, V_SCALAR_CONST = 3, V_SCALAR_PAIR = 4 };
+enum Variant { V_F2_CONSTM = 0, V_F2 = 1, V_F2H = 2, V_SCALAR_CONST = 3, V_SCALAR_PAIR = 4, V_F2H_CONSTM = 5 };
 struct DirectPlan {
     int variant;
     float eps2_f, mass_f;
@@ -386,6 +386,11 @@ __device__ __forceinline__ f2_t f2_sub(f2_t a, f2_t b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+    f2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
     f2_t r;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -586,14 +591,16 @@ __device__ __forceinline__ void pair_h2_scalar(float xi, float yi, float zi, flo
     }
 }
 
-template <int WANT, int HMODE>
+template <int WANT, int HMODE, bool CONSTM>
 __global__ void __launch_bounds__(DT, PNBX_MINB)
 direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h2, int64_t n_src,
                   const Vec4<float>* __restrict__ tgt, const float* __restrict__ tgt_h2, int64_t m, int64_t self_base,
                   int plan_slot, int tiles_per_split, double* __restrict__ out_pot,
                   double* __restrict__ out_acc) {
     __shared__ Pair8 s_src[STAGES][TILEP];
-    if (c_plans[plan_slot].variant != V_F2H) return;
+    // CONSTM: all source masses equal (decided on the device like in direct_kernel_f2): the mass leaves the loops and is
+    // applied once at the end; the spline's "pair inside its softening radius" zeroes 1/r instead of the mass
+    if (c_plans[plan_slot].variant != (CONSTM ? V_F2H_CONSTM : V_F2H)) return;
     __shared__ alignas(16) float2 s_h2[STAGES][TILEP];
     __shared__ alignas(8) uint64_t s_full[STAGES];
     const int tid = threadIdx.x;
@@ -654,13 +661,16 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
         const int cnt = (int)(n_pairs - q0 < TILEP ? n_pairs - q0 : TILEP);
         const int64_t j0 = 2 * q0;
         const bool diag = (j0 < blk_hi) && (j0 + 2 * cnt > blk_lo);
-        if (!diag && cnt == TILEP) {
+        const bool has_pad = CONSTM && (n_src & 1) && tile == n_tiles - 1;  // the zero-mass pad needs its mass
+        if (!diag && cnt == TILEP && !has_pad) {
             f2_t ax[TPT], ay[TPT], az[TPT], p[TPT];
 #pragma unroll
             for (int k = 0; k < TPT; ++k) ax[k] = ay[k] = az[k] = p[k] = 0ull;  // {+0.f, +0.f}
             // spline: bit g of `inside` = some pair of records [8g, 8g+8) lies inside its softening radius for one of
             // this lane's targets; pass 2 revisits only those groups (TILEP / 8 = 32 groups: one 32-bit mask per lane)
-            unsigned inside = 0u;
+            unsigned inside[TPT];  // one group mask per target: pass 2 touches only (group, target) pairs that need it
+#pragma unroll
+            for (int k = 0; k < TPT; ++k) inside[k] = 0u;
             static_assert(TILEP == 256, "the group mask of the spline pass assumes 32 groups of 8 pair records");
 #pragma unroll UNROLL_F2
             for (int q = 0; q < TILEP; ++q) {
@@ -678,18 +688,25 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
                     r2 = f2_fma(dz, dz, r2);
                     float ra, rb;
                     f2_unpack(r2, ra, rb);
+                    float ia_r = rsqrt_fast(ra), ib_r = rsqrt_fast(rb);
                     f2_t mm = v.w;
                     if (HMODE == 2) {
-                        float m0, m1;
-                        f2_unpack(v.w, m0, m1);
                         const bool ia = ra < h2a, ib = rb < h2b;  // r < h: left to pass 2 (no add-then-subtract)
-                        inside |= (ia | ib) ? gbit : 0u;
-                        mm = f2_pack(ia ? 0.f : m0, ib ? 0.f : m1);
+                        inside[k] |= (ia | ib) ? gbit : 0u;
+                        if (CONSTM) {  // zero 1/r: the pair then adds nothing to either sum
+                            ia_r = ia ? 0.f : ia_r;
+                            ib_r = ib ? 0.f : ib_r;
+                        } else {
+                            float m0, m1;
+                            f2_unpack(v.w, m0, m1);
+                            mm = f2_pack(ia ? 0.f : m0, ib ? 0.f : m1);
+                        }
                     }
-                    const f2_t rinv = f2_pack(rsqrt_fast(ra), rsqrt_fast(rb));
-                    if (WANT & PNBX_WANT_POT) p[k] = f2_fma(mm, rinv, p[k]);
+                    const f2_t rinv = f2_pack(ia_r, ib_r);
+                    if (WANT & PNBX_WANT_POT) p[k] = CONSTM ? f2_add(p[k], rinv) : f2_fma(mm, rinv, p[k]);
                     if (WANT & PNBX_WANT_ACC) {
-                        const f2_t g = f2_mul(f2_mul(mm, rinv), f2_mul(rinv, rinv));
+                        const f2_t rr = f2_mul(rinv, rinv);
+                        const f2_t g = CONSTM ? f2_mul(rr, rinv) : f2_mul(f2_mul(mm, rinv), rr);
                         ax[k] = f2_fma(dx, g, ax[k]);
                         ay[k] = f2_fma(dy, g, ay[k]);
                         az[k] = f2_fma(dz, g, az[k]);
@@ -712,19 +729,20 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
             if (HMODE == 2) {
                 // pass 2: W2 terms of the pairs with r < h, only in the flagged groups of 8 pair records (each lane walks
                 // its own set bits; the predicate inside pair_h2_scalar is pass 1's, bit for bit)
-                while (inside) {
-                    const int g = __ffs((int)inside) - 1;
-                    inside &= inside - 1u;
-#pragma unroll 2
-                    for (int q = 8 * g; q < 8 * g + 8; ++q) {
-                        const Pair8 pr = s_src[st][q];
-                        const float2 hh = s_h2[st][q];
 #pragma unroll
-                        for (int k = 0; k < TPT; ++k) {
-                            pair_h2_scalar<WANT, 2, true>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2[k], pr.x0, pr.y0, pr.z0, pr.m0, hh.x, false,
-                                                          sax[k], say[k], saz[k], sp[k]);
-                            pair_h2_scalar<WANT, 2, true>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2[k], pr.x1, pr.y1, pr.z1, pr.m1, hh.y, false,
-                                                          sax[k], say[k], saz[k], sp[k]);
+                for (int k = 0; k < TPT; ++k) {
+                    unsigned todo = inside[k];
+                    while (todo) {
+                        const int g = __ffs((int)todo) - 1;
+                        todo &= todo - 1u;
+#pragma unroll 2
+                        for (int q = 8 * g; q < 8 * g + 8; ++q) {
+                            const Pair8 pr = s_src[st][q];
+                            const float2 hh = s_h2[st][q];
+                            pair_h2_scalar<WANT, 2, true>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2[k], pr.x0, pr.y0, pr.z0,
+                                                          CONSTM ? 1.f : pr.m0, hh.x, false, sax[k], say[k], saz[k], sp[k]);
+                            pair_h2_scalar<WANT, 2, true>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2[k], pr.x1, pr.y1, pr.z1,
+                                                          CONSTM ? 1.f : pr.m1, hh.y, false, sax[k], say[k], saz[k], sp[k]);
                         }
                     }
                 }
@@ -746,7 +764,7 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
                 const float2 hh = s_h2[st][j >> 1];
                 const bool odd = j & 1;
                 const float sx = odd ? pr.x1 : pr.x0, sy = odd ? pr.y1 : pr.y0, sz = odd ? pr.z1 : pr.z0;
-                const float sm = odd ? pr.m1 : pr.m0, hs2 = odd ? hh.y : hh.x;
+                const float sm = CONSTM ? 1.f : (odd ? pr.m1 : pr.m0), hs2 = odd ? hh.y : hh.x;
                 const int64_t gj = j0 + j;
 #pragma unroll
                 for (int k = 0; k < TPT; ++k)
@@ -762,14 +780,15 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
         __syncthreads();
     }
     const int64_t split_off = (int64_t)blockIdx.y * m;
+    const double ms = CONSTM ? c_plans[plan_slot].mass_d : 1.0;
 #pragma unroll
     for (int k = 0; k < TPT; ++k) {
         int64_t i = tgt_base + k * DT + tid;
         if (i < m) {
-            if (WANT & PNBX_WANT_POT) out_pot[split_off + i] = P[k];
+            if (WANT & PNBX_WANT_POT) out_pot[split_off + i] = P[k] * ms;
             if (WANT & PNBX_WANT_ACC) {
                 double* a = out_acc + 3 * (split_off + i);
-                a[0] = Ax[k]; a[1] = Ay[k]; a[2] = Az[k];
+                a[0] = Ax[k] * ms; a[1] = Ay[k] * ms; a[2] = Az[k] * ms;
             }
         }
     }
@@ -896,7 +915,7 @@ __global__ void classify_direct(ClassifyArgs c, DirectPlan* __restrict__ plan) {
         // clamps at 0 anyway (h <= 0 is Newtonian), at-points Plummer uses max(h_j, 0) (direct.rs:560); Plummer in
         // self mode with a negative softening (max(h_i, h_j) of signed values) stays on the scalar kernel.
         const bool f2h_ok = c.packed && c.allow_f2h && (c.kernel == PNBX_KERNEL_SPLINE || !c.self || hmn >= 0.0);
-        p.variant = f2h_ok ? V_F2H : V_SCALAR_PAIR;
+        p.variant = !f2h_ok ? V_SCALAR_PAIR : (c.allow_constm && mmn == mmx) ? V_F2H_CONSTM : V_F2H;
     }
     *plan = p;
 }
@@ -1059,10 +1078,14 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
         if (may_f2) PNBX_LAUNCH((direct_kernel_f2<W, false>), grid, DT, 0, s, sp, n, tp, m, sb, pl, tiles_per_split, kp, ka);        \
         if (may_f2h) {                                                                                                 \
             const float* th2 = self ? srch2.get() + tgt_begin : nullptr; /* at-points targets have no softening */    \
-            if (kernel == PNBX_KERNEL_PLUMMER)                                                                         \
-                PNBX_LAUNCH((direct_kernel_f2h<W, 1>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
-            else                                                                                                       \
-                PNBX_LAUNCH((direct_kernel_f2h<W, 2>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
+            const bool cm = may_f2_constm, gm = may_f2; /* equal / general masses: same host knowledge as for f2 */    \
+            if (kernel == PNBX_KERNEL_PLUMMER) {                                                                       \
+                if (cm) PNBX_LAUNCH((direct_kernel_f2h<W, 1, true>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
+                if (gm) PNBX_LAUNCH((direct_kernel_f2h<W, 1, false>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
+            } else {                                                                                                   \
+                if (cm) PNBX_LAUNCH((direct_kernel_f2h<W, 2, true>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
+                if (gm) PNBX_LAUNCH((direct_kernel_f2h<W, 2, false>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
+            }                                                                                                          \
         }                                                                                                              \
     }
         PNBX_F2(1) PNBX_F2(2) PNBX_F2(3)

@@ -204,3 +204,28 @@ def test_packed_per_pair_kernels_match_scalar_kernels_full_tiles():
         p = r.direct_potentials_py(pos, m, 0, h, kernel)
         a = r.direct_accelerations_py(pos, m, 0, h, kernel)
         assert rms_rel(p, p_s) < TOL32 and rms_rel_vec(a, a_s) < TOL32
+
+
+@pytest.mark.parametrize("n", [20011, 20012, 700])
+def test_packed_per_pair_kernels_equal_mass_variant(n):
+    # equal source masses + per-particle softenings take the equal-mass variant of the packed per-pair kernels (mass
+    # factored out, the spline zeroes 1/r of inside pairs): odd N (zero-mass pad in the last tile), even N, N < one tile;
+    # unit masses (masses=None) are equal masses too
+    r = backend()
+    pos, m = hernquist(n, seed=191)
+    h = np.random.default_rng(192).uniform(0.002, 0.2, n)
+    m = np.full(n, 0.37 / n)
+    idx = np.random.default_rng(194).choice(n, min(n, 1200), replace=False)
+    for kernel in (0, 1):
+        p_s, a_s = O.direct(pos, m, h, kernel=kernel)
+        assert rms_rel(r.direct_potentials_py(pos, m, 0, h, kernel), p_s) < TOL32
+        assert rms_rel_vec(r.direct_accelerations_py(pos, m, 0, h, kernel), a_s) < TOL32
+        # targets exactly on sources (r = 0 pairs inside their own softening), as in the general-mass test above; an
+        # offset of 1e-3 at |x| ~ 70 would only test the fp32 resolution of box-centred coordinates (4e-6)
+        q = np.ascontiguousarray(pos[idx])
+        p_o, a_o = O.direct(pos, m, h, targets=q, kernel=kernel)
+        assert rms_rel(r.direct_potentials_at_points_py(pos, q, m, 0, h, kernel), p_o) < TOL32
+        assert rms_rel_vec(r.direct_accelerations_at_points_py(pos, q, m, 0, h, kernel), a_o) < TOL32
+        p_u, a_u = O.direct(pos, None, h, kernel=kernel)
+        assert rms_rel(r.direct_potentials_py(pos, None, 0, h, kernel), p_u) < TOL32
+        assert rms_rel_vec(r.direct_accelerations_py(pos, None, 0, h, kernel), a_u) < TOL32
