@@ -154,3 +154,19 @@ def test_direct_calls_are_stream_ordered_without_host_syncs():
         p_o, a_o = O.direct(pos, dm.cpu().numpy(), h, kernel=k)
         tol = 1e-5 if h is not None else 1e-3  # unsoftened fp32: close pairs below the coordinate resolution
         assert rms_rel(p.cpu().numpy(), p_o) < tol and rms_rel_vec(a.cpu().numpy(), a_o) < tol
+
+
+def test_gravity_init_aliases_contiguous_float64_inputs():
+    # documented difference: the reference's Gravity.__init__ copies (`astype`, base.py:199-200); here
+    # float64 C-contiguous inputs are NOT copied — the device upload at call time is the copy — so a caller who mutates
+    # its arrays between construction and a call sees the mutation. Other dtypes / layouts are converted (= copied).
+    from pynbodyext.gravity import Gravity
+    pos, m = plummer(2000, seed=5)
+    g = Gravity(pos, m)
+    assert g.pos is pos or np.shares_memory(g.pos, pos)
+    before = g.direct_potentials(precision="f64")
+    pos *= 2.0  # same shape, all separations doubled -> potentials halved
+    after = g.direct_potentials(precision="f64")
+    assert np.allclose(after, 0.5 * before, rtol=1e-12)
+    g32 = Gravity(pos.astype(np.float32), m)  # converted: an independent float64 copy
+    assert not np.shares_memory(g32.pos, pos)
