@@ -123,8 +123,8 @@ void run_ranks(const std::vector<int>& devs, HostBarrier& bar, F&& body) {
     std::vector<RankError> errs((size_t)W);
     std::vector<std::thread> th;
     th.reserve((size_t)W);
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int stage_threads = (int)std::max(1u, std::min(8u, hw / (unsigned)W));
+    // host cores are shared by the rank threads and their staging lanes
+    const int stage_threads = std::max(1, std::min(8, (available_cpus() - W) / W));
     for (int r = 0; r < W; ++r) {
         th.emplace_back([&, r] {
             try {
