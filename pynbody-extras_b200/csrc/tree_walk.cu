@@ -37,6 +37,8 @@ struct Vec4T {
     T x, y, z, w;
 };
 
+constexpr int WALK_VISIT_COST = 16;  // hybrid split: one node visit of a warp ~ 16 pair-loop iterations
+
 template <class T>
 struct WalkArgs {
     const NodeRec* rec;
@@ -66,6 +68,13 @@ struct WalkArgs {
     double* out_pot;
     double* out_acc;
     OutSlices slices;         // multi-device self evaluation: results go to the owner of the ORIGINAL index (peer stores)
+    // hybrid evaluation of query points (tree_walk): a warp of the lane-per-target kernel whose walk outgrows `budget`
+    // (node visits x WALK_VISIT_COST + particles of the leaves it loops over) gives up, appends its points to
+    // `over_list` and leaves them to the warp-per-target kernel, which reads its target count from the device
+    int budget;               // INT_MAX: no limit
+    uint32_t* over_list;      // points handed over (any order), *n_over of them
+    int* n_over;
+    const int* n_front;       // warp-per-target kernel, nullable: number of valid entries of torder (else m)
 };
 
 // One node record = four 16-byte loads issued TOGETHER at the top of a visit. Left to the compiler, the loads of the
@@ -244,6 +253,7 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
     }
     double P = 0.0, Ax = 0.0, Ay = 0.0, Az = 0.0;
     long long n_visit = 0, n_accept = 0, n_leaf = 0, n_leafp = 0, n_wvisit = 0;
+    int cost = 0;  // warp-uniform
 
     bool active = valid;
     int resume = INT_MIN;
@@ -252,6 +262,18 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
         const NodeRec c = load_rec(a.rec + idx);  // one 64-byte record: one memory round trip per visit
         const NodeRec& gm = c;
         if (!active && resume == idx) active = true;
+        if (WANT != 0 && sizeof(T) == 4) {
+            cost += c.kind >= 0 ? WALK_VISIT_COST + c.kind : WALK_VISIT_COST;
+            if (cost > a.budget) {  // hand this warp's points over to the warp-per-target kernel (query points only)
+                const unsigned vm = __ballot_sync(FULL, valid);
+                const int lane = threadIdx.x & 31;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(a.n_over, __popc(vm));
+                base = __shfl_sync(FULL, base, 0);
+                if (valid) a.over_list[base + __popc(vm & ((1u << lane) - 1u))] = (uint32_t)oslot;
+                return;
+            }
+        }
         if (WANT == 0) {  // a leaf-run record stands for `nleaf` reference nodes (tree.cuh)
             const int nodes = c.kind >= 0 ? c.nleaf : 1;
             if (active) n_visit += nodes;
@@ -462,7 +484,7 @@ __global__ void __launch_bounds__(WT) walk_wpt_kernel(const WalkArgs<float> a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t k = ((int64_t)blockIdx.x * WT + threadIdx.x) >> 5;  // one target per warp
-    if (k >= a.m) return;  // whole warp
+    if (k >= (a.n_front ? (int64_t)*a.n_front : a.m)) return;  // whole warp
     double tx, ty, tz, th64 = 0.0;
     int skip = -1;
     int64_t oslot;
@@ -721,6 +743,7 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         a.kernel = t.kernel;
         a.out_pot = d_pot; a.out_acc = d_acc;
         a.slices = slices ? *slices : OutSlices{};
+        a.budget = INT_MAX; a.over_list = nullptr; a.n_over = nullptr; a.n_front = nullptr;
     };
     const int order = std::max(1, t.order);  // order 0 and 1 are both monopoles
     tm.begin("octree.walk");
@@ -750,7 +773,34 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         const char* wpt_env = getenv("PNBX_WPT_MAX_TARGETS");
         const int64_t wpt_max = wpt_env ? atoll(wpt_env) : (int64_t)(self ? 16384 : 131072);
         const bool wpt = wpt_basis <= wpt_max;
-        if (wpt) {
+        // Larger point sets, HYBRID: the lane-per-target kernel's time on a query grid is set by its slowest warps —
+        // 32 neighbouring points of a sparse log-spaced grid whose paths diverge (the warp visits the union), or points
+        // in a softened core where the gate opens whole subtrees. A warp whose walk outgrows the budget (a few times
+        // the cost of a typical warp of a self evaluation) gives up and its points are walked one per warp instead.
+        // Which warps give up is a deterministic function of their 32 points. Measured (zoom set, ms, lane / warp /
+        // hybrid): N = 1e7: 2.5e5 points 7.7 / 12.9 / 5.7, 1e6 points 9.9 / 52.3 / 9.1; N = 1e8: 2.5e5 points
+        // 141 / 21.2 / 24.0, 1e6 points 129 / 79.3 / 52.8. Giving up early on warps with few active lanes (sampled
+        // every budget / 8) made it slower (1e6 points: 13.2 at N = 1e7, 63.3 at N = 1e8): not built.
+        const char* hy_env = getenv("PNBX_WALK_HYBRID_COST");
+        const int64_t budget = hy_env ? atoll(hy_env) : 64000;
+        if (!wpt && !self && budget > 0) {
+            DevBuf<uint32_t> over((size_t)m_walk, s);
+            DevBuf<int> n_over(1, s);
+            PNBX_CUDA(cudaMemsetAsync(n_over.p, 0, sizeof(int), s));
+            a.budget = (int)std::min<int64_t>(budget, INT_MAX / 2);
+            a.over_list = over.p;
+            a.n_over = n_over.p;
+            if (!any_soft) launch_walk<float, 0>(order, want, a, s);
+            else if (t.kernel == PNBX_KERNEL_SPLINE) launch_walk<float, 2>(order, want, a, s);
+            else launch_walk<float, 1>(order, want, a, s);
+            a.budget = INT_MAX;
+            a.torder = over.p;
+            a.cyc_block = 0;
+            a.n_front = n_over.p;
+            if (!any_soft) launch_walk_wpt<0>(order, want, a, s);
+            else if (t.kernel == PNBX_KERNEL_SPLINE) launch_walk_wpt<2>(order, want, a, s);
+            else launch_walk_wpt<1>(order, want, a, s);
+        } else if (wpt) {
             if (!any_soft) launch_walk_wpt<0>(order, want, a, s);
             else if (t.kernel == PNBX_KERNEL_SPLINE) launch_walk_wpt<2>(order, want, a, s);
             else launch_walk_wpt<1>(order, want, a, s);

@@ -17,11 +17,15 @@ T = np.load(os.path.join(HERE, "golden", "tree_golden.npz"))
 DIRECT = (("newton", None, False), ("plummer", 0, True), ("spline", 1, True))
 
 
-@pytest.fixture(autouse=True, params=["lane", "warp"])
+@pytest.fixture(autouse=True, params=["lane", "warp", "hybrid"])
 def walk_kernel_choice(request, monkeypatch):
-    """Every test runs with both fp32 walk kernels: one target per lane (large calls) and one target per warp (calls
-    with few targets; PNBX_WPT_MAX_TARGETS is the switch-over size, default 16384 particles / 131072 query points)."""
-    monkeypatch.setenv("PNBX_WPT_MAX_TARGETS", "0" if request.param == "lane" else "4000000000")
+    """Every test runs with the fp32 walk kernels in all three arrangements: one target per lane (large calls), one
+    target per warp (calls with few targets; PNBX_WPT_MAX_TARGETS is the switch-over size, default 16384 particles /
+    131072 query points), and — query points only — the hybrid split of larger point sets (warps of 32 points whose walk in the
+    lane-per-target kernel outgrows PNBX_WALK_HYBRID_COST are handed to the warp-per-target kernel; lowered here so
+    that both parts are populated at test sizes)."""
+    monkeypatch.setenv("PNBX_WPT_MAX_TARGETS", "4000000000" if request.param == "warp" else "0")
+    monkeypatch.setenv("PNBX_WALK_HYBRID_COST", "6000" if request.param == "hybrid" else "0")
 
 
 def rms_rel_vec(a, ref):

@@ -15,11 +15,15 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["lane", "warp"])
+@pytest.fixture(autouse=True, params=["lane", "warp", "hybrid"])
 def walk_kernel_choice(request, monkeypatch):
-    """Every test runs with both fp32 walk kernels: one target per lane (large calls) and one target per warp (calls
-    with few targets; PNBX_WPT_MAX_TARGETS is the switch-over size, default 16384 particles / 131072 query points)."""
-    monkeypatch.setenv("PNBX_WPT_MAX_TARGETS", "0" if request.param == "lane" else "4000000000")
+    """Every test runs with the fp32 walk kernels in all three arrangements: one target per lane (large calls), one
+    target per warp (calls with few targets; PNBX_WPT_MAX_TARGETS is the switch-over size, default 16384 particles /
+    131072 query points), and — query points only — the hybrid split of larger point sets (warps of 32 points whose walk in the
+    lane-per-target kernel outgrows PNBX_WALK_HYBRID_COST are handed to the warp-per-target kernel; lowered here so
+    that both parts are populated at test sizes)."""
+    monkeypatch.setenv("PNBX_WPT_MAX_TARGETS", "4000000000" if request.param == "warp" else "0")
+    monkeypatch.setenv("PNBX_WALK_HYBRID_COST", "6000" if request.param == "hybrid" else "0")
 
 TOL32 = 1e-5
 TOL64 = 1e-11
@@ -147,6 +151,40 @@ def test_at_points_matches_oracle_tree(order):
     assert rms_rel(p64, p_o) < TOL64 and rms_rel_vec(a64, a_o) < TOL64
     assert rms_rel(g.potentials_at_points(q, 0.7), p_o) < TOL32
     assert rms_rel_vec(g.accelerations_at_points(q, 0.7), a_o) < TOL32
+
+
+def test_hybrid_point_walk_is_a_per_point_choice_of_the_two_kernels(monkeypatch):
+    # Larger query sets start in the lane-per-target kernel; a warp (32 consecutive points in path-key order) whose walk
+    # outgrows PNBX_WALK_HYBRID_COST gives up and its points are walked one per warp by the other kernel. Each point's
+    # value is bit-equal to what the kernel that finished it gives for the whole set.
+    from benchmarks.synthetic import rz_grid_targets, zoom_set
+    n = 200_000
+    pos, m, h = zoom_set(n, seed=4)
+    q = rz_grid_targets(30_011, seed=5)  # not a multiple of 32: a partial trailing warp
+    t = R().Octree(pos, m, 8, 3, h, 1)
+
+    def run(wpt, cost):
+        monkeypatch.setenv("PNBX_WPT_MAX_TARGETS", wpt)
+        monkeypatch.setenv("PNBX_WALK_HYBRID_COST", cost)
+        return t._eval(q, 0.7, 3)
+
+    lane, warp = run("0", "0"), run("4000000000", "0")
+    mixed = 0
+    for cost in ("2000", "8000", "16000", "32000", "64000", "1000000000"):
+        hyb = run("0", cost)
+        eq_lane = (hyb[0] == lane[0]) & (hyb[1] == lane[1]).all(1)
+        eq_warp = (hyb[0] == warp[0]) & (hyb[1] == warp[1]).all(1)
+        assert (eq_lane | eq_warp).all()
+        mixed += bool((~eq_lane).any() and (~eq_warp).any())
+    assert mixed >= 2  # thresholds at which both classes are populated
+    o = O.Tree(pos, m, 8, 3, h, 1)
+    sub = np.random.default_rng(3).choice(q.shape[0], 400, replace=False)
+    p_o, a_o = o.eval(0.7, targets=q[sub])
+    hyb = run("0", "16000")
+    assert rms_rel(hyb[0][sub], p_o) < TOL32 and rms_rel_vec(hyb[1][sub], a_o) < TOL32
+    # default threshold, default switch-over: same values again from whichever kernels are chosen, to fp32 accuracy
+    monkeypatch.delenv("PNBX_WPT_MAX_TARGETS"); monkeypatch.delenv("PNBX_WALK_HYBRID_COST")
+    assert rms_rel(t.potentials_at_points(q[sub], 0.7), p_o) < TOL32
 
 
 @pytest.mark.parametrize("kernel", [0, 1])
