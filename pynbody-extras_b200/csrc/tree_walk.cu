@@ -209,7 +209,7 @@ __device__ __forceinline__ Vec4T<double> load_src<double>(const WalkArgs<double>
 // SMODE: 0 = no softening anywhere (no per-particle h, no hmax gate), 1 = Plummer, 2 = cubic spline,
 //        3 = decided at run time (float64 verification mode and the counting pass).
 // WANT == 0 is the counting pass: traversal decisions only, totals into a.counters.
-template <int ORDER, int WANT, class T, int SMODE>
+template <int ORDER, int WANT, class T, int SMODE, bool BUDGET = false>
 __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_WALK_MINB) walk_kernel(const WalkArgs<T> a) {
     constexpr int DORD = (WANT & PNBX_WANT_ACC) ? (ORDER < 1 ? 1 : ORDER) : (ORDER < 2 ? 0 : ORDER);
     constexpr unsigned FULL = 0xffffffffu;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
         const NodeRec c = load_rec(a.rec + idx);  // one 64-byte record: one memory round trip per visit
         const NodeRec& gm = c;
         if (!active && resume == idx) active = true;
-        if (WANT != 0 && sizeof(T) == 4) {
+        if constexpr (BUDGET) {  // separate instantiation: the self evaluations' loop does not carry the counter
             cost += c.kind >= 0 ? WALK_VISIT_COST + c.kind : WALK_VISIT_COST;
             if (cost > a.budget) {  // hand this warp's points over to the warp-per-target kernel (query points only)
                 const unsigned vm = __ballot_sync(FULL, valid);
@@ -453,12 +453,12 @@ __global__ void __launch_bounds__(WT, (ORDER >= 4 || sizeof(T) == 8) ? 4 : PNBX_
     }
 }
 
-template <class T, int SMODE>
+template <class T, int SMODE, bool BUDGET = false>
 void launch_walk(int order, int want, const WalkArgs<T>& a, cudaStream_t s) {
     const unsigned grid = (unsigned)std::max<int64_t>(1, ceil_div(a.m, WT));
 #define PNBX_W(O, W)                                                        \
     if (order == O && want == W) {                                          \
-        PNBX_LAUNCH((walk_kernel<O, W, T, SMODE>), grid, WT, 0, s, a);      \
+        PNBX_LAUNCH((walk_kernel<O, W, T, SMODE, BUDGET>), grid, WT, 0, s, a); \
         return;                                                             \
     }
     PNBX_W(1, 1) PNBX_W(1, 2) PNBX_W(1, 3)
@@ -790,9 +790,9 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
             a.budget = (int)std::min<int64_t>(budget, INT_MAX / 2);
             a.over_list = over.p;
             a.n_over = n_over.p;
-            if (!any_soft) launch_walk<float, 0>(order, want, a, s);
-            else if (t.kernel == PNBX_KERNEL_SPLINE) launch_walk<float, 2>(order, want, a, s);
-            else launch_walk<float, 1>(order, want, a, s);
+            if (!any_soft) launch_walk<float, 0, true>(order, want, a, s);
+            else if (t.kernel == PNBX_KERNEL_SPLINE) launch_walk<float, 2, true>(order, want, a, s);
+            else launch_walk<float, 1, true>(order, want, a, s);
             a.budget = INT_MAX;
             a.torder = over.p;
             a.cyc_block = 0;
