@@ -804,8 +804,11 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(n, world), "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, **e2e_extra, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
-            "parity_pin": "oracle-only (the Rust reference cannot be built in this image; the oracle is a line-by-line "
-                          "port checked by ORACLE_REVIEW.md and independent symbolic tests)",
+            "parity_pin": "reference source executed (no Rust toolchain in this image, so the reference binary cannot be "
+                          "built; tests/golden/make_reference_exec.py translates the reference's own kernel.rs / direct.rs "
+                          "/ multipole.rs / tree.rs walk functions to Python mechanically and runs them: "
+                          "tests/golden/reference_exec.npz, 250 arrays, oracle bit-exact against them in "
+                          "tests/test_oracle_vs_reference_source.py; ORACLE_REVIEW.md lists the line-by-line review)",
             "tflops_20flop": FLOP_PER_INTERACTION * value * 1e9 / 1e12, "tree": tree, "tree_1e8": tree_1e8,
         }
         emit(line)

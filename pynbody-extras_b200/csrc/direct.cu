@@ -14,6 +14,8 @@
 #include <cfloat>
 #include <mutex>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "spline.cuh"
 
@@ -591,11 +593,83 @@ __device__ __forceinline__ void pair_h2_scalar(float xi, float yi, float zi, flo
     }
 }
 
+// Extents of one source tile (TILEP pair records): squared-softening range and bounding box. A target block compares
+// them with its own extents once per tile and picks a cheaper inner loop when the whole tile allows it:
+//   Plummer, tile h_max <= block h_min: max(h_i, h_j) = h_i for every pair -> the softening is a per-target constant
+//   Plummer, tile h_min >= block h_max: max(h_i, h_j) = h_j -> the addend comes straight from the source record
+//   spline, boxes further apart than the largest softening radius of either side: every pair is Newtonian
+// Each pair gets bit for bit the value the general loop would give it. Whole-array self calls sort the particles so
+// that nearly all tiles qualify (run_direct: by softening for Plummer, along a Morton curve for the spline).
+struct alignas(16) TileMeta {
+    float h2min, h2max, lox, loy, loz, hix, hiy, hiz;
+};
+enum Regime { R_GENERAL = 0, R_TARGET_H = 1, R_SOURCE_H = 2, R_FAR = 3 };
+
+// The packed pass over one full tile. REGIME is a compile-time copy of the loop for each case above.
+template <int WANT, int HMODE, bool CONSTM, int REGIME>
+__device__ __forceinline__ void f2h_tile(const Pair8* __restrict__ t_src, const float2* __restrict__ t_h2,
+                                         const f2_t (&xi)[TPT], const f2_t (&yi)[TPT], const f2_t (&zi)[TPT],
+                                         const float (&th2f)[TPT], f2_t (&ax)[TPT], f2_t (&ay)[TPT], f2_t (&az)[TPT],
+                                         f2_t (&p)[TPT], unsigned (&inside)[TPT]) {
+    const f2_t tiny2 = f2_pack(FLT_MIN, FLT_MIN);
+#pragma unroll UNROLL_F2
+    for (int q = 0; q < TILEP; ++q) {
+        const ulonglong4 v = *reinterpret_cast<const ulonglong4*>(&t_src[q]);  // {x0x1, y0y1, z0z1, m0m1}
+        float2 hh = make_float2(0.f, 0.f);
+        if (REGIME == R_GENERAL || REGIME == R_SOURCE_H) hh = t_h2[q];
+        const unsigned gbit = 1u << (q >> 3);
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) {
+            const f2_t dx = f2_sub(v.x, xi[k]), dy = f2_sub(v.y, yi[k]), dz = f2_sub(v.z, zi[k]);
+            // th2f[k] = max(th2[k], FLT_MIN) for Plummer (the + R2_TINY folded into the softening), th2[k] for
+            // the spline: one max per source, h^2 = max(h_s^2, h_t^2)
+            float h2a = 0.f, h2b = 0.f;
+            f2_t add = tiny2;
+            if (REGIME == R_GENERAL) {
+                h2a = fmaxf(hh.x, th2f[k]); h2b = fmaxf(hh.y, th2f[k]);
+                if (HMODE == 1) add = f2_pack(h2a, h2b);
+            } else if (REGIME == R_TARGET_H) {
+                add = f2_pack(th2f[k], th2f[k]);
+            } else if (REGIME == R_SOURCE_H) {
+                add = f2_pack(hh.x, hh.y);
+            }
+            f2_t r2 = f2_fma(dx, dx, add);
+            r2 = f2_fma(dy, dy, r2);
+            r2 = f2_fma(dz, dz, r2);
+            float ra, rb;
+            f2_unpack(r2, ra, rb);
+            float ia_r = rsqrt_fast(ra), ib_r = rsqrt_fast(rb);
+            f2_t mm = v.w;
+            if (HMODE == 2 && REGIME == R_GENERAL) {
+                const bool ia = ra < h2a, ib = rb < h2b;  // r < h: left to pass 2 (no add-then-subtract)
+                inside[k] |= (ia | ib) ? gbit : 0u;
+                if (CONSTM) {  // zero 1/r: the pair then adds nothing to either sum
+                    ia_r = ia ? 0.f : ia_r;
+                    ib_r = ib ? 0.f : ib_r;
+                } else {
+                    float m0, m1;
+                    f2_unpack(v.w, m0, m1);
+                    mm = f2_pack(ia ? 0.f : m0, ib ? 0.f : m1);
+                }
+            }
+            const f2_t rinv = f2_pack(ia_r, ib_r);
+            if (WANT & PNBX_WANT_POT) p[k] = CONSTM ? f2_add(p[k], rinv) : f2_fma(mm, rinv, p[k]);
+            if (WANT & PNBX_WANT_ACC) {
+                const f2_t rr = f2_mul(rinv, rinv);
+                const f2_t g = CONSTM ? f2_mul(rr, rinv) : f2_mul(f2_mul(mm, rinv), rr);
+                ax[k] = f2_fma(dx, g, ax[k]);
+                ay[k] = f2_fma(dy, g, ay[k]);
+                az[k] = f2_fma(dz, g, az[k]);
+            }
+        }
+    }
+}
+
 template <int WANT, int HMODE, bool CONSTM>
 __global__ void __launch_bounds__(DT, PNBX_MINB)
-direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h2, int64_t n_src,
-                  const Vec4<float>* __restrict__ tgt, const float* __restrict__ tgt_h2, int64_t m, int64_t self_base,
-                  int plan_slot, int tiles_per_split, double* __restrict__ out_pot,
+direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h2, const TileMeta* __restrict__ tile_meta,
+                  int64_t n_src, const Vec4<float>* __restrict__ tgt, const float* __restrict__ tgt_h2, int64_t m,
+                  int64_t self_base, int plan_slot, int tiles_per_split, double* __restrict__ out_pot,
                   double* __restrict__ out_acc) {
     __shared__ Pair8 s_src[STAGES][TILEP];
     // CONSTM: all source masses equal (decided on the device like in direct_kernel_f2): the mass leaves the loops and is
@@ -625,16 +699,43 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
     // results are never stored, so their index does not matter)
     const int64_t g0 = self_base >= 0 ? self_base + tgt_base + tid : INT64_MIN / 2;
     auto lo = [](f2_t v) { float a, b; f2_unpack(v, a, b); return a; };
-    const f2_t tiny2 = f2_pack(FLT_MIN, FLT_MIN);
     double Ax[TPT], Ay[TPT], Az[TPT], P[TPT];
 #pragma unroll
     for (int k = 0; k < TPT; ++k) Ax[k] = Ay[k] = Az[k] = P[k] = 0.0;
 
+    // extents of this block's targets: {h2 min, -h2 max, x min, -x max, y min, -y max, z min, -z max}, all as minima
+    __shared__ float s_ext[8][DT / 32];
+    float ext[8];
+    {
+        ext[0] = th2f[0]; ext[1] = -th2f[0];
+        ext[2] = lo(xi[0]); ext[3] = -ext[2]; ext[4] = lo(yi[0]); ext[5] = -ext[4]; ext[6] = lo(zi[0]); ext[7] = -ext[6];
+#pragma unroll
+        for (int k = 1; k < TPT; ++k) {
+            ext[0] = fminf(ext[0], th2f[k]); ext[1] = fminf(ext[1], -th2f[k]);
+            ext[2] = fminf(ext[2], lo(xi[k])); ext[3] = fminf(ext[3], -lo(xi[k]));
+            ext[4] = fminf(ext[4], lo(yi[k])); ext[5] = fminf(ext[5], -lo(yi[k]));
+            ext[6] = fminf(ext[6], lo(zi[k])); ext[7] = fminf(ext[7], -lo(zi[k]));
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ext[r] = fminf(ext[r], __shfl_xor_sync(0xffffffffu, ext[r], o));
+            if ((tid & 31) == 0) s_ext[r][tid >> 5] = ext[r];
+        }
+    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        float v = s_ext[r][0];
+#pragma unroll
+        for (int w = 1; w < DT / 32; ++w) v = fminf(v, s_ext[r][w]);
+        ext[r] = v;
+    }
+    const float blk_h2min = ext[0], blk_h2max = -ext[1];
     auto issue = [&](int64_t tile) {
         int st = (int)((tile - tile_begin) % STAGES);
         int64_t q0 = tile * TILEP;
@@ -672,47 +773,32 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
 #pragma unroll
             for (int k = 0; k < TPT; ++k) inside[k] = 0u;
             static_assert(TILEP == 256, "the group mask of the spline pass assumes 32 groups of 8 pair records");
-#pragma unroll UNROLL_F2
-            for (int q = 0; q < TILEP; ++q) {
-                const ulonglong4 v = *reinterpret_cast<const ulonglong4*>(&s_src[st][q]);  // {x0x1, y0y1, z0z1, m0m1}
-                const float2 hh = s_h2[st][q];
-                const unsigned gbit = 1u << (q >> 3);
-#pragma unroll
-                for (int k = 0; k < TPT; ++k) {
-                    const f2_t dx = f2_sub(v.x, xi[k]), dy = f2_sub(v.y, yi[k]), dz = f2_sub(v.z, zi[k]);
-                    // th2f[k] = max(th2[k], FLT_MIN) for Plummer (the + R2_TINY folded into the softening), th2[k] for
-                    // the spline: one max per source, h^2 = max(h_s^2, h_t^2)
-                    const float h2a = fmaxf(hh.x, th2f[k]), h2b = fmaxf(hh.y, th2f[k]);
-                    f2_t r2 = f2_fma(dx, dx, HMODE == 1 ? f2_pack(h2a, h2b) : tiny2);
-                    r2 = f2_fma(dy, dy, r2);
-                    r2 = f2_fma(dz, dz, r2);
-                    float ra, rb;
-                    f2_unpack(r2, ra, rb);
-                    float ia_r = rsqrt_fast(ra), ib_r = rsqrt_fast(rb);
-                    f2_t mm = v.w;
-                    if (HMODE == 2) {
-                        const bool ia = ra < h2a, ib = rb < h2b;  // r < h: left to pass 2 (no add-then-subtract)
-                        inside[k] |= (ia | ib) ? gbit : 0u;
-                        if (CONSTM) {  // zero 1/r: the pair then adds nothing to either sum
-                            ia_r = ia ? 0.f : ia_r;
-                            ib_r = ib ? 0.f : ib_r;
-                        } else {
-                            float m0, m1;
-                            f2_unpack(v.w, m0, m1);
-                            mm = f2_pack(ia ? 0.f : m0, ib ? 0.f : m1);
-                        }
-                    }
-                    const f2_t rinv = f2_pack(ia_r, ib_r);
-                    if (WANT & PNBX_WANT_POT) p[k] = CONSTM ? f2_add(p[k], rinv) : f2_fma(mm, rinv, p[k]);
-                    if (WANT & PNBX_WANT_ACC) {
-                        const f2_t rr = f2_mul(rinv, rinv);
-                        const f2_t g = CONSTM ? f2_mul(rr, rinv) : f2_mul(f2_mul(mm, rinv), rr);
-                        ax[k] = f2_fma(dx, g, ax[k]);
-                        ay[k] = f2_fma(dy, g, ay[k]);
-                        az[k] = f2_fma(dz, g, az[k]);
-                    }
+            int regime = R_GENERAL;
+            if (tile_meta) {
+                const float4 ma = __ldg(reinterpret_cast<const float4*>(tile_meta + tile));
+                const float4 mb = __ldg(reinterpret_cast<const float4*>(tile_meta + tile) + 1);
+                if (HMODE == 1) {
+                    if (ma.y <= blk_h2min) regime = R_TARGET_H;
+                    else if (ma.x >= blk_h2max) regime = R_SOURCE_H;
+                } else {
+                    // gap between the two boxes, component-wise: {lo - blk_hi, blk_lo - hi}
+                    const float gx = fmaxf(0.f, fmaxf(ma.z + ext[3], ext[2] - mb.y));   // tile.lox - blk.hix, blk.lox - tile.hix
+                    const float gy = fmaxf(0.f, fmaxf(ma.w + ext[5], ext[4] - mb.z));
+                    const float gz = fmaxf(0.f, fmaxf(mb.x + ext[7], ext[6] - mb.w));
+                    const float gap2 = gx * gx + gy * gy + gz * gz;
+                    // margin: the pair distances are rounded fp32 sums (relative error ~1e-6), the test must imply
+                    // r2 >= h2 for the rounded values of every pair
+                    if (gap2 > fmaxf(ma.y, blk_h2max) * 1.0001f + FLT_MIN) regime = R_FAR;
                 }
             }
+            if (HMODE == 1 && regime == R_TARGET_H)
+                f2h_tile<WANT, HMODE, CONSTM, R_TARGET_H>(s_src[st], s_h2[st], xi, yi, zi, th2f, ax, ay, az, p, inside);
+            else if (HMODE == 1 && regime == R_SOURCE_H)
+                f2h_tile<WANT, HMODE, CONSTM, R_SOURCE_H>(s_src[st], s_h2[st], xi, yi, zi, th2f, ax, ay, az, p, inside);
+            else if (HMODE == 2 && regime == R_FAR)
+                f2h_tile<WANT, HMODE, CONSTM, R_FAR>(s_src[st], s_h2[st], xi, yi, zi, th2f, ax, ay, az, p, inside);
+            else
+                f2h_tile<WANT, HMODE, CONSTM, R_GENERAL>(s_src[st], s_h2[st], xi, yi, zi, th2f, ax, ay, az, p, inside);
             float sax[TPT], say[TPT], saz[TPT], sp[TPT];
 #pragma unroll
             for (int k = 0; k < TPT; ++k) {
@@ -791,6 +877,99 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
                 a[0] = Ax[k] * ms; a[1] = Ay[k] * ms; a[2] = Az[k] * ms;
             }
         }
+    }
+}
+
+// Extents of every source tile for direct_kernel_f2h (one block per tile, one thread per pair record).
+__global__ void tile_extents(const Pair8* __restrict__ src, const float* __restrict__ h2, int64_t n_pairs,
+                             TileMeta* __restrict__ out) {
+    __shared__ float s_red[8][TILEP / 32];
+    const int64_t q = (int64_t)blockIdx.x * TILEP + threadIdx.x;
+    float v[8] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};
+    if (q < n_pairs) {
+        const Pair8 pr = src[q];
+        const float ha = h2[2 * q], hb = h2[2 * q + 1];
+        v[0] = fminf(ha, hb); v[1] = -fmaxf(ha, hb);
+        v[2] = fminf(pr.x0, pr.x1); v[3] = -fmaxf(pr.x0, pr.x1);
+        v[4] = fminf(pr.y0, pr.y1); v[5] = -fmaxf(pr.y0, pr.y1);
+        v[6] = fminf(pr.z0, pr.z1); v[7] = -fmaxf(pr.z0, pr.z1);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[r] = fminf(v[r], __shfl_xor_sync(0xffffffffu, v[r], o));
+        if ((threadIdx.x & 31) == 0) s_red[r][threadIdx.x >> 5] = v[r];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            for (int w = 0; w < TILEP / 32; ++w) v[r] = fminf(v[r], s_red[r][w]);
+        TileMeta t;
+        t.h2min = v[0]; t.h2max = -v[1];
+        t.lox = v[2]; t.hix = -v[3]; t.loy = v[4]; t.hiy = -v[5]; t.loz = v[6]; t.hiz = -v[7];
+        out[blockIdx.x] = t;
+    }
+}
+
+// Sort keys of the whole-array self calls with per-particle softenings (run_direct): Plummer — the clamped softening
+// (non-negative floats order like their bit patterns); spline — a 30-bit Morton code inside the bounding box.
+__device__ __forceinline__ uint32_t spread10(uint32_t x) {
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+__global__ void direct_sort_keys(const double* __restrict__ pos, const double* __restrict__ h, int64_t n,
+                                 const double* __restrict__ bbox6, int by_position, uint32_t* __restrict__ key,
+                                 uint32_t* __restrict__ idx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    idx[i] = (uint32_t)i;
+    if (!by_position) {
+        key[i] = __float_as_uint((float)fmax(h[i], 0.0));
+        return;
+    }
+    uint32_t c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double lo = bbox6[d], ext = bbox6[3 + d] - lo;
+        double u = ext > 0.0 ? (pos[3 * i + d] - lo) / ext : 0.0;
+        u = fmin(fmax(u, 0.0), 1.0);
+        c[d] = min(1023u, (uint32_t)(u * 1024.0));
+    }
+    key[i] = spread10(c[0]) | (spread10(c[1]) << 1) | (spread10(c[2]) << 2);
+}
+__global__ void gather_sorted(const uint32_t* __restrict__ perm, int64_t n, const double* __restrict__ pos,
+                              const double* __restrict__ mass, const double* __restrict__ h, double* __restrict__ pos_s,
+                              double* __restrict__ mass_s, double* __restrict__ h_s) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t i = perm[k];
+    pos_s[3 * k] = pos[3 * i]; pos_s[3 * k + 1] = pos[3 * i + 1]; pos_s[3 * k + 2] = pos[3 * i + 2];
+    if (mass) mass_s[k] = mass[i];
+    h_s[k] = h[i];
+}
+// results of the sorted sweep back to the caller's order (also sums the source splits, in split order)
+__global__ void scatter_results(const uint32_t* __restrict__ perm, int64_t m, int splits, const double* __restrict__ pot_s,
+                                const double* __restrict__ acc_s, double* __restrict__ pot, double* __restrict__ acc) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const int64_t i = perm[k];
+    if (pot) {
+        double v = 0.0;
+        for (int sidx = 0; sidx < splits; ++sidx) v += pot_s[(int64_t)sidx * m + k];
+        pot[i] = v;
+    }
+    if (acc) {
+        double x = 0.0, y = 0.0, z = 0.0;
+        for (int sidx = 0; sidx < splits; ++sidx) {
+            const double* a = acc_s + 3 * ((int64_t)sidx * m + k);
+            x += a[0]; y += a[1]; z += a[2];
+        }
+        acc[3 * i] = x; acc[3 * i + 1] = y; acc[3 * i + 2] = z;
     }
 }
 
@@ -1016,10 +1195,41 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     const bool may_scalar_const = !packed;
     const bool may_scalar_pair = may_pair && (!packed || !allow_f2h || (kernel == PNBX_KERNEL_PLUMMER && self));
 
+    // ---- whole-array self calls with per-particle softenings: sort the particles so that whole (target block, source
+    // tile) combinations resolve max(h_i, h_j) / "is any pair inside its softening radius" at once (TileMeta) — by
+    // softening for Plummer, along a Morton curve for the spline. The sweep then runs on the sorted copies and
+    // scatter_results puts the sums back in the caller's order. The sort is stable: constant softenings keep the
+    // caller's order under the Plummer key.
+    const char* sort_env = getenv("PNBX_DIRECT_SORT_MIN");
+    const int64_t sort_min = sort_env ? atoll(sort_env) : 65536;
+    const bool sorted = sizeof(T) == 4 && may_f2h && self && tgt_begin == 0 && m == n && n >= sort_min && sort_min >= 0;
+    DevBuf<uint32_t> perm;
+    DevBuf<double> pos_s, mass_s, h_s;
+    if (sorted) {
+        DevBuf<uint32_t> key((size_t)n, s), key_s((size_t)n, s), idx((size_t)n, s);
+        perm.alloc((size_t)n, s);
+        PNBX_LAUNCH(direct_sort_keys, (unsigned)ceil_div(n, 256), 256, 0, s, d_pos, d_h, n, bbox.get(),
+                    kernel == PNBX_KERNEL_SPLINE ? 1 : 0, key.get(), idx.get());
+        size_t bytes = 0;
+        PNBX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key.get(), key_s.get(), idx.get(), perm.get(), (int)n, 0, 32, s));
+        DevBuf<uint8_t> tmp(bytes, s);
+        PNBX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), bytes, key.get(), key_s.get(), idx.get(), perm.get(), (int)n, 0, 32, s));
+        ++launch_counter();
+        pos_s.alloc((size_t)3 * n, s);
+        if (d_mass) mass_s.alloc((size_t)n, s);
+        h_s.alloc((size_t)n, s);
+        PNBX_LAUNCH(gather_sorted, (unsigned)ceil_div(n, 256), 256, 0, s, perm.get(), n, d_pos, d_mass, d_h, pos_s.get(),
+                    mass_s.get(), h_s.get());
+        d_pos = pos_s.get();
+        if (d_mass) d_mass = mass_s.get();
+        d_h = h_s.get();
+    }
+
     // ---- packing
     DevBuf<Vec4<T>> src4;
     DevBuf<Pair8> srcp;
     DevBuf<float> srch2;
+    DevBuf<TileMeta> tmeta;
     DevBuf<T> srch;
     if (packed) {
         srcp.alloc((size_t)(n + 1) / 2, s);
@@ -1028,6 +1238,11 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
             const int64_t np = ((n + 1) / 2) * 2 + 4;  // whole pair records + room for the 16-byte rounding of the bulk copy
             srch2.alloc((size_t)np, s);
             PNBX_LAUNCH(pack_h2, (unsigned)ceil_div(np, 256), 256, 0, s, d_h, n, np, srch2.get());
+            if (!getenv("PNBX_DIRECT_NO_REGIMES")) {
+                const int64_t n_pairs = (n + 1) / 2;
+                tmeta.alloc((size_t)ceil_div(n_pairs, TILEP), s);
+                PNBX_LAUNCH(tile_extents, (unsigned)ceil_div(n_pairs, TILEP), TILEP, 0, s, srcp.get(), srch2.get(), n_pairs, tmeta.get());
+            }
         }
     }
     if (may_scalar_const || may_scalar_pair) {
@@ -1060,7 +1275,7 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     DevBuf<double> part_pot, part_acc;
     double* kp = d_pot;
     double* ka = d_acc;
-    if (splits > 1) {
+    if (splits > 1 || sorted) {
         if (want & PNBX_WANT_POT) { part_pot.alloc((size_t)(splits * m), s); kp = part_pot.get(); }
         if (want & PNBX_WANT_ACC) { part_acc.alloc((size_t)(splits * m * 3), s); ka = part_acc.get(); }
     }
@@ -1079,12 +1294,13 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
         if (may_f2h) {                                                                                                 \
             const float* th2 = self ? srch2.get() + tgt_begin : nullptr; /* at-points targets have no softening */    \
             const bool cm = may_f2_constm, gm = may_f2; /* equal / general masses: same host knowledge as for f2 */    \
+            const TileMeta* tmp_ = tmeta.get();                                                                        \
             if (kernel == PNBX_KERNEL_PLUMMER) {                                                                       \
-                if (cm) PNBX_LAUNCH((direct_kernel_f2h<W, 1, true>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
-                if (gm) PNBX_LAUNCH((direct_kernel_f2h<W, 1, false>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
+                if (cm) PNBX_LAUNCH((direct_kernel_f2h<W, 1, true>), grid, DT, 0, s, sp, srch2.get(), tmp_, n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
+                if (gm) PNBX_LAUNCH((direct_kernel_f2h<W, 1, false>), grid, DT, 0, s, sp, srch2.get(), tmp_, n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
             } else {                                                                                                   \
-                if (cm) PNBX_LAUNCH((direct_kernel_f2h<W, 2, true>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
-                if (gm) PNBX_LAUNCH((direct_kernel_f2h<W, 2, false>), grid, DT, 0, s, sp, srch2.get(), n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
+                if (cm) PNBX_LAUNCH((direct_kernel_f2h<W, 2, true>), grid, DT, 0, s, sp, srch2.get(), tmp_, n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
+                if (gm) PNBX_LAUNCH((direct_kernel_f2h<W, 2, false>), grid, DT, 0, s, sp, srch2.get(), tmp_, n, tp, th2, m, sb, pl, tiles_per_split, kp, ka); \
             }                                                                                                          \
         }                                                                                                              \
     }
@@ -1101,7 +1317,12 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     release_plan_slot(ex.device, s, slot);
     kernel_events().end(s);
     PNBX_CUDA(cudaGetLastError());
-    if (splits > 1) {
+    if (sorted) {
+        PNBX_LAUNCH(scatter_results, (unsigned)ceil_div(m, 256), 256, 0, s, perm.get(), m, (int)splits,
+                    (want & PNBX_WANT_POT) ? kp : nullptr, (want & PNBX_WANT_ACC) ? ka : nullptr,
+                    (want & PNBX_WANT_POT) ? d_pot : nullptr, (want & PNBX_WANT_ACC) ? d_acc : nullptr);
+        PNBX_CUDA(cudaGetLastError());
+    } else if (splits > 1) {
         if (want & PNBX_WANT_POT)
             PNBX_LAUNCH(reduce_splits, (unsigned)ceil_div(m, 256), 256, 0, s, kp, m, (int)splits, d_pot);
         if (want & PNBX_WANT_ACC)

@@ -16,6 +16,14 @@ TOL32 = 1e-5
 TOL64 = 1e-11
 
 
+@pytest.fixture(autouse=True, params=["caller_order", "sorted"])
+def direct_particle_order(request, monkeypatch):
+    """Whole-array self calls with per-particle softenings sort the particles (by softening for Plummer, along a Morton
+    curve for the spline) so that whole source tiles resolve max(h_i, h_j) / the r < h test at once; the default only
+    does so from 65536 particles (PNBX_DIRECT_SORT_MIN). Every test runs both ways."""
+    monkeypatch.setenv("PNBX_DIRECT_SORT_MIN", "0" if request.param == "sorted" else "-1")
+
+
 def rms_rel_vec(a, ref):
     return np.sqrt((((a - ref) ** 2).sum(1) / (ref ** 2).sum(1)).mean())
 
@@ -229,3 +237,62 @@ def test_packed_per_pair_kernels_equal_mass_variant(n):
         p_u, a_u = O.direct(pos, None, h, kernel=kernel)
         assert rms_rel(r.direct_potentials_py(pos, None, 0, h, kernel), p_u) < TOL32
         assert rms_rel_vec(r.direct_accelerations_py(pos, None, 0, h, kernel), a_u) < TOL32
+
+
+def max_rel_vec(a, ref):
+    return (np.linalg.norm(a - ref, axis=1) / np.linalg.norm(ref, axis=1)).max()
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("pattern", ["random_small", "families", "one_wide"])
+@pytest.mark.parametrize("equal_mass", [True, False])
+def test_tile_regimes_match_oracle(kernel, pattern, equal_mass):
+    # direct_kernel_f2h picks a cheaper loop for whole (target block, source tile) combinations: Plummer with the tile's
+    # softenings all below / all above the block's (max(h_i, h_j) known), spline with the two bounding boxes further
+    # apart than every softening radius involved (Newtonian). 80 source tiles here; softenings well below the
+    # particle spacing so that most spline tiles qualify once the particles are Morton-sorted, contiguous families of
+    # equal softening (the usual snapshot layout: the regimes apply without sorting), and one particle with a huge
+    # softening radius (its tile and block never qualify, every pair with it is inside). A pair wrongly treated as
+    # Newtonian would show up as an O(1) error on its two particles: the check is on the MAXIMUM relative error.
+    r = backend()
+    n = 40_001
+    pos, m = hernquist(n, seed=7)
+    rng = np.random.default_rng(11)
+    if not equal_mass:
+        m = m * rng.uniform(0.5, 2.0, n)
+    if pattern == "random_small":
+        h = rng.uniform(0.005, 0.02, n)
+    elif pattern == "families":
+        h = np.concatenate([np.full(n // 3, 0.01), np.full(n // 3, 0.04), np.full(n - 2 * (n // 3), 0.002)])
+    else:
+        h = rng.uniform(0.005, 0.02, n)
+        h[12345] = 50.0
+    p_o, a_o = O.direct(pos, m, h, kernel=kernel)
+    p = r.direct_potentials_py(pos, m, 0, h, kernel)
+    a = r.direct_accelerations_py(pos, m, 0, h, kernel)
+    assert rms_rel(p, p_o) < TOL32 and rms_rel_vec(a, a_o) < TOL32
+    assert np.abs((p - p_o) / p_o).max() < 1e-4 and max_rel_vec(a, a_o) < 2e-3
+    # at-points: h = max(h_j, 0), every Plummer tile takes its softening from the source records
+    q = hernquist(3000, seed=8)[0]  # independent points: no separation below the fp32 resolution of the coordinates
+    p_q, a_q = O.direct(pos, m, h, targets=q, kernel=kernel)
+    assert np.abs((r.direct_potentials_at_points_py(pos, q, m, 0, h, kernel) - p_q) / p_q).max() < 1e-4
+    assert max_rel_vec(r.direct_accelerations_at_points_py(pos, q, m, 0, h, kernel), a_q) < 2e-3
+
+
+def test_sorted_sweep_is_a_reordering_of_the_same_pair_terms(monkeypatch):
+    # sorting changes the summation order only: sorted and caller-order results agree to fp32 accumulation accuracy,
+    # and constant softenings are not reordered at all by the (stable) Plummer key: bit-equal
+    r = backend()
+    n = 70_000
+    pos, m = hernquist(n, seed=3)
+    h = np.random.default_rng(4).uniform(0.005, 0.02, n)
+    out = {}
+    for mode in ("-1", "0"):
+        monkeypatch.setenv("PNBX_DIRECT_SORT_MIN", mode)
+        out[mode] = (r.direct_accelerations_py(pos, m, 0, h, 0), r.direct_accelerations_py(pos, m, 0, h, 1),
+                     r.direct_accelerations_py(pos, m, 0, np.full(n, 0.01), 0))
+    for k in (0, 1):
+        assert 0 < max_rel_vec(out["0"][k], out["-1"][k]) < 1e-4
+    assert np.array_equal(out["0"][2], out["-1"][2])
+    monkeypatch.delenv("PNBX_DIRECT_SORT_MIN")  # default: sorted from 65536 particles
+    assert np.array_equal(r.direct_accelerations_py(pos, m, 0, h, 1), out["0"][1])
