@@ -685,15 +685,16 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
     const int64_t tgt_base = (int64_t)blockIdx.x * (DT * TPT);
 
     f2_t xi[TPT], yi[TPT], zi[TPT];
-    float th2[TPT], th2f[TPT];
+    // squared target softening; Plummer folds the + R2_TINY in: max(h_s^2, h_t^2, FLT_MIN) = max(h_s^2, th2f)
+    float th2f[TPT];
 #pragma unroll
     for (int k = 0; k < TPT; ++k) {
         int64_t i = tgt_base + k * DT + tid;
         if (i > m - 1) i = m - 1;
         Vec4<float> t = tgt[i];
         xi[k] = f2_pack(t.x, t.x); yi[k] = f2_pack(t.y, t.y); zi[k] = f2_pack(t.z, t.z);
-        th2[k] = tgt_h2 ? tgt_h2[i] : 0.f;
-        th2f[k] = HMODE == 1 ? fmaxf(th2[k], FLT_MIN) : th2[k];
+        const float t2 = tgt_h2 ? tgt_h2[i] : 0.f;
+        th2f[k] = HMODE == 1 ? fmaxf(t2, FLT_MIN) : t2;
     }
     // global source index of this thread's k-th target: g0 + k*DT (lanes past the end are clamped duplicates whose
     // results are never stored, so their index does not matter)
@@ -705,8 +706,8 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
 
     // extents of this block's targets: {h2 min, -h2 max, x min, -x max, y min, -y max, z min, -z max}, all as minima
     __shared__ float s_ext[8][DT / 32];
-    float ext[8];
     {
+        float ext[8];
         ext[0] = th2f[0]; ext[1] = -th2f[0];
         ext[2] = lo(xi[0]); ext[3] = -ext[2]; ext[4] = lo(yi[0]); ext[5] = -ext[4]; ext[6] = lo(zi[0]); ext[7] = -ext[6];
 #pragma unroll
@@ -728,14 +729,15 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // the block's extents stay in shared memory (read once per tile): no registers held across the packed loops
+    __shared__ float s_blk[8];
+    if (tid < 8) {
+        float v = s_ext[tid][0];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        float v = s_ext[r][0];
-#pragma unroll
-        for (int w = 1; w < DT / 32; ++w) v = fminf(v, s_ext[r][w]);
-        ext[r] = v;
+        for (int w = 1; w < DT / 32; ++w) v = fminf(v, s_ext[tid][w]);
+        s_blk[tid] = v;
     }
-    const float blk_h2min = ext[0], blk_h2max = -ext[1];
+    __syncthreads();
     auto issue = [&](int64_t tile) {
         int st = (int)((tile - tile_begin) % STAGES);
         int64_t q0 = tile * TILEP;
@@ -777,14 +779,15 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
             if (tile_meta) {
                 const float4 ma = __ldg(reinterpret_cast<const float4*>(tile_meta + tile));
                 const float4 mb = __ldg(reinterpret_cast<const float4*>(tile_meta + tile) + 1);
+                const float blk_h2min = s_blk[0], blk_h2max = -s_blk[1];
                 if (HMODE == 1) {
                     if (ma.y <= blk_h2min) regime = R_TARGET_H;
                     else if (ma.x >= blk_h2max) regime = R_SOURCE_H;
                 } else {
                     // gap between the two boxes, component-wise: {lo - blk_hi, blk_lo - hi}
-                    const float gx = fmaxf(0.f, fmaxf(ma.z + ext[3], ext[2] - mb.y));   // tile.lox - blk.hix, blk.lox - tile.hix
-                    const float gy = fmaxf(0.f, fmaxf(ma.w + ext[5], ext[4] - mb.z));
-                    const float gz = fmaxf(0.f, fmaxf(mb.x + ext[7], ext[6] - mb.w));
+                    const float gx = fmaxf(0.f, fmaxf(ma.z + s_blk[3], s_blk[2] - mb.y));   // tile.lox - blk.hix, blk.lox - tile.hix
+                    const float gy = fmaxf(0.f, fmaxf(ma.w + s_blk[5], s_blk[4] - mb.z));
+                    const float gz = fmaxf(0.f, fmaxf(mb.x + s_blk[7], s_blk[6] - mb.w));
                     const float gap2 = gx * gx + gy * gy + gz * gz;
                     // margin: the pair distances are rounded fp32 sums (relative error ~1e-6), the test must imply
                     // r2 >= h2 for the rounded values of every pair
@@ -825,9 +828,9 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
                         for (int q = 8 * g; q < 8 * g + 8; ++q) {
                             const Pair8 pr = s_src[st][q];
                             const float2 hh = s_h2[st][q];
-                            pair_h2_scalar<WANT, 2, true>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2[k], pr.x0, pr.y0, pr.z0,
+                            pair_h2_scalar<WANT, 2, true>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2f[k], pr.x0, pr.y0, pr.z0,
                                                           CONSTM ? 1.f : pr.m0, hh.x, false, sax[k], say[k], saz[k], sp[k]);
-                            pair_h2_scalar<WANT, 2, true>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2[k], pr.x1, pr.y1, pr.z1,
+                            pair_h2_scalar<WANT, 2, true>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2f[k], pr.x1, pr.y1, pr.z1,
                                                           CONSTM ? 1.f : pr.m1, hh.y, false, sax[k], say[k], saz[k], sp[k]);
                         }
                     }
@@ -854,7 +857,7 @@ direct_kernel_f2h(const Pair8* __restrict__ src, const float* __restrict__ src_h
                 const int64_t gj = j0 + j;
 #pragma unroll
                 for (int k = 0; k < TPT; ++k)
-                    pair_h2_scalar<WANT, HMODE, false>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2[k], sx, sy, sz, sm, hs2, gj == g0 + k * DT, ax[k],
+                    pair_h2_scalar<WANT, HMODE, false>(lo(xi[k]), lo(yi[k]), lo(zi[k]), th2f[k], sx, sy, sz, sm, hs2, gj == g0 + k * DT, ax[k],
                                                        ay[k], az[k], p[k]);
             }
 #pragma unroll
