@@ -953,7 +953,7 @@ __global__ void gather_sorted(const uint32_t* __restrict__ perm, int64_t n, cons
     const int64_t i = perm[k];
     pos_s[3 * k] = pos[3 * i]; pos_s[3 * k + 1] = pos[3 * i + 1]; pos_s[3 * k + 2] = pos[3 * i + 2];
     if (mass) mass_s[k] = mass[i];
-    h_s[k] = h[i];
+    if (h) h_s[k] = h[i];
 }
 // results of the sorted sweep back to the caller's order (also sums the source splits, in split order)
 __global__ void scatter_results(const uint32_t* __restrict__ perm, int64_t m, int splits, const double* __restrict__ pot_s,
@@ -1198,35 +1198,53 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     const bool may_scalar_const = !packed;
     const bool may_scalar_pair = may_pair && (!packed || !allow_f2h || (kernel == PNBX_KERNEL_PLUMMER && self));
 
-    // ---- whole-array self calls with per-particle softenings: sort the particles so that whole (target block, source
-    // tile) combinations resolve max(h_i, h_j) / "is any pair inside its softening radius" at once (TileMeta) — by
-    // softening for Plummer, along a Morton curve for the spline. The sweep then runs on the sorted copies and
-    // scatter_results puts the sums back in the caller's order. The sort is stable: constant softenings keep the
-    // caller's order under the Plummer key.
+    // ---- per-particle softenings: sort the particles so that whole (target block, source tile) combinations resolve
+    // max(h_i, h_j) / "is any pair inside its softening radius" at once (TileMeta).
+    //   whole-array self calls: sources = targets, by softening for Plummer, along a Morton curve for the spline;
+    //   spline at points: the order of the sources is free, so they are Morton-sorted, and so are the points (inside
+    //     the sources' bounding box) — Plummer at points needs no order (every tile takes its softening from the
+    //     source records).
+    // The sweep runs on the sorted copies and scatter_results puts the sums back in the caller's order. The sort is
+    // stable: constant softenings keep the caller's order under the Plummer key.
     const char* sort_env = getenv("PNBX_DIRECT_SORT_MIN");
     const int64_t sort_min = sort_env ? atoll(sort_env) : 65536;
-    const bool sorted = sizeof(T) == 4 && may_f2h && self && tgt_begin == 0 && m == n && n >= sort_min && sort_min >= 0;
-    DevBuf<uint32_t> perm;
-    DevBuf<double> pos_s, mass_s, h_s;
-    if (sorted) {
-        DevBuf<uint32_t> key((size_t)n, s), key_s((size_t)n, s), idx((size_t)n, s);
-        perm.alloc((size_t)n, s);
-        PNBX_LAUNCH(direct_sort_keys, (unsigned)ceil_div(n, 256), 256, 0, s, d_pos, d_h, n, bbox.get(),
-                    kernel == PNBX_KERNEL_SPLINE ? 1 : 0, key.get(), idx.get());
+    const bool can_sort = sizeof(T) == 4 && may_f2h && n >= sort_min && sort_min >= 0;
+    const bool sorted = can_sort && self && tgt_begin == 0 && m == n;           // sources and targets, one permutation
+    const bool sorted_pts = can_sort && !self && kernel == PNBX_KERNEL_SPLINE && m < ((int64_t)1 << 31);  // sources; points with their own
+    DevBuf<uint32_t> perm;  // sorted target position -> caller's target index
+    DevBuf<double> pos_s, mass_s, h_s, tgt_s;
+    auto sort_perm = [&](const double* p3, const double* hh, int64_t cnt, bool by_position, DevBuf<uint32_t>& out) {
+        DevBuf<uint32_t> key((size_t)cnt, s), key_s((size_t)cnt, s), idx((size_t)cnt, s);
+        out.alloc((size_t)cnt, s);
+        PNBX_LAUNCH(direct_sort_keys, (unsigned)ceil_div(cnt, 256), 256, 0, s, p3, hh, cnt, bbox.get(), by_position ? 1 : 0,
+                    key.get(), idx.get());
         size_t bytes = 0;
-        PNBX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key.get(), key_s.get(), idx.get(), perm.get(), (int)n, 0, 32, s));
+        PNBX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key.get(), key_s.get(), idx.get(), out.get(), (int)cnt, 0, 32, s));
         DevBuf<uint8_t> tmp(bytes, s);
-        PNBX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), bytes, key.get(), key_s.get(), idx.get(), perm.get(), (int)n, 0, 32, s));
+        PNBX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), bytes, key.get(), key_s.get(), idx.get(), out.get(), (int)cnt, 0, 32, s));
         ++launch_counter();
+    };
+    if (sorted || sorted_pts) {
+        DevBuf<uint32_t> sperm_own;
+        DevBuf<uint32_t>& sperm = sorted ? perm : sperm_own;
+        sort_perm(d_pos, d_h, n, kernel == PNBX_KERNEL_SPLINE, sperm);
         pos_s.alloc((size_t)3 * n, s);
         if (d_mass) mass_s.alloc((size_t)n, s);
         h_s.alloc((size_t)n, s);
-        PNBX_LAUNCH(gather_sorted, (unsigned)ceil_div(n, 256), 256, 0, s, perm.get(), n, d_pos, d_mass, d_h, pos_s.get(),
+        PNBX_LAUNCH(gather_sorted, (unsigned)ceil_div(n, 256), 256, 0, s, sperm.get(), n, d_pos, d_mass, d_h, pos_s.get(),
                     mass_s.get(), h_s.get());
         d_pos = pos_s.get();
         if (d_mass) d_mass = mass_s.get();
         d_h = h_s.get();
+        if (sorted_pts) {
+            sort_perm(d_tgt, nullptr, m, true, perm);
+            tgt_s.alloc((size_t)3 * m, s);
+            PNBX_LAUNCH(gather_sorted, (unsigned)ceil_div(m, 256), 256, 0, s, perm.get(), m, d_tgt, nullptr, nullptr, tgt_s.get(),
+                        nullptr, nullptr);
+            d_tgt = tgt_s.get();
+        }
     }
+    const bool scatter_back = sorted || sorted_pts;
 
     // ---- packing
     DevBuf<Vec4<T>> src4;
@@ -1278,7 +1296,7 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     DevBuf<double> part_pot, part_acc;
     double* kp = d_pot;
     double* ka = d_acc;
-    if (splits > 1 || sorted) {
+    if (splits > 1 || scatter_back) {
         if (want & PNBX_WANT_POT) { part_pot.alloc((size_t)(splits * m), s); kp = part_pot.get(); }
         if (want & PNBX_WANT_ACC) { part_acc.alloc((size_t)(splits * m * 3), s); ka = part_acc.get(); }
     }
@@ -1320,7 +1338,7 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     release_plan_slot(ex.device, s, slot);
     kernel_events().end(s);
     PNBX_CUDA(cudaGetLastError());
-    if (sorted) {
+    if (scatter_back) {
         PNBX_LAUNCH(scatter_results, (unsigned)ceil_div(m, 256), 256, 0, s, perm.get(), m, (int)splits,
                     (want & PNBX_WANT_POT) ? kp : nullptr, (want & PNBX_WANT_ACC) ? ka : nullptr,
                     (want & PNBX_WANT_POT) ? d_pot : nullptr, (want & PNBX_WANT_ACC) ? d_acc : nullptr);
