@@ -181,7 +181,6 @@ struct Arena {
 // staging.cu: host<->device copies; large PAGEABLE host arrays are staged through pinned buffers by a few host threads
 void copy_h2d(void* dev, const void* host, size_t bytes, const Exec& ex);
 void copy_d2h(void* host, const void* dev, size_t bytes, const Exec& ex);
-int available_cpus();  // CPUs in this process's affinity mask
 void set_staging_threads_for_this_thread(int n);  // multi-device rank threads share the host cores; < 0 = default
 
 // Input array that may live on the host (copied in, like gravity.rs:154-180) or on the device.

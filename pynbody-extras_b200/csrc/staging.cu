@@ -5,7 +5,6 @@
 // that a few host threads memcpy into their own pinned double buffers and DMA from there on their own streams, so
 // the host-side memcpy of one chunk overlaps the DMA of another (the reference's `threads` argument sized a rayon
 // pool; here host threads only ever move bytes). Pinned inputs and small arrays take the plain path.
-#include <sched.h>
 
 #include <cstring>
 #include <mutex>
@@ -35,28 +34,12 @@ std::mutex g_mu[MAX_DEVICES];
 Lane g_lanes[MAX_DEVICES][MAX_THREADS];
 thread_local int tl_threads_override = -1;
 
-}  // namespace
-
-// CPUs this process may run on (cgroup / affinity mask), not the machine's core count: a container with 16 of 192
-// cores must not start 64 staging threads.
-int available_cpus() {
-    cpu_set_t set;
-    CPU_ZERO(&set);
-    if (sched_getaffinity(0, sizeof(set), &set) == 0) {
-        const int n = CPU_COUNT(&set);
-        if (n > 0) return n;
-    }
-    const unsigned hw = std::thread::hardware_concurrency();
-    return hw ? (int)hw : 1;
-}
-
-namespace {
 int staging_threads() {
     static const int n = [] {
         const char* e = getenv("PNBX_STAGING_THREADS");
         int v = e ? atoi(e) : 8;  // measured: 4 threads ~25 GB/s, 8 threads ~50 GB/s (pinned-memory speed)
-        const int hw = available_cpus();
-        if (v > hw) v = hw;
+        unsigned hw = std::thread::hardware_concurrency();
+        if (hw && (unsigned)v > hw) v = (int)hw;
         return std::max(0, std::min(v, MAX_THREADS));
     }();
     return tl_threads_override >= 0 ? std::min(tl_threads_override, n) : n;
