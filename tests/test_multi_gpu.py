@@ -140,3 +140,28 @@ def test_bad_device_list_is_an_error(multi_env):
     pos, m = hernquist(2000, seed=2)
     with pytest.raises(ValueError, match="PNBX_DEVICES"):
         r.direct_potentials_py(pos, m)
+
+
+def test_point_evaluation_hybrid_walk_multi_equals_single(multi_env, monkeypatch):
+    # larger point sets: lane-per-target walk with a cost budget per warp + hand-over to the warp-per-target kernel.
+    # The devices take blocks of 256 points of the path-key order, i.e. whole warps of the single-device call: the same
+    # warps give up, so the assembled result is bit-identical to the single-device one.
+    import pynbodyext._rust as r
+    on, off = multi_env
+    monkeypatch.setenv("PNBX_WPT_MAX_TARGETS", "0")
+    monkeypatch.setenv("PNBX_WALK_HYBRID_COST", "6000")
+    n = 300_007
+    pos, m, h = nfw_disc(n, seed=5)
+    q = rz_grid_targets(20_000, seed=6, rmax=1.0)
+    off()
+    t1 = r.Octree(pos, m, 8, 3, h, 1, device=0)
+    p1, a1 = t1._eval(q, 0.7, 3)
+    monkeypatch.setenv("PNBX_WALK_HYBRID_COST", "0")
+    p_lane = t1._eval(q, 0.7, 1)[0]
+    monkeypatch.setenv("PNBX_WALK_HYBRID_COST", "6000")
+    assert 0 < (p1 != p_lane).sum() < q.shape[0]  # some warps were handed over, not all
+    on()
+    tm = r.Octree(pos, m, 8, 3, h, 1)
+    pm, am = tm._eval(q, 0.7, 3)
+    assert np.array_equal(pm, p1) and np.array_equal(am, a1)
+    del tm, t1
