@@ -783,7 +783,7 @@ void tree_walk(const pnbx_tree_impl& t, const Exec& ex, const double* d_tgt, int
         // every budget / 8) made it slower (1e6 points: 13.2 at N = 1e7, 63.3 at N = 1e8): not built.
         const char* hy_env = getenv("PNBX_WALK_HYBRID_COST");
         const int64_t budget = hy_env ? atoll(hy_env) : 64000;
-        if (!wpt && !self && budget > 0) {
+        if (!wpt && !self && budget > 0 && m_walk < ((int64_t)1 << 31)) {  // the hand-over count is an int
             DevBuf<uint32_t> over((size_t)m_walk, s);
             DevBuf<int> n_over(1, s);
             PNBX_CUDA(cudaMemsetAsync(n_over.p, 0, sizeof(int), s));
