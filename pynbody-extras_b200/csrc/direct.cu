@@ -925,14 +925,17 @@ __device__ __forceinline__ uint32_t spread10(uint32_t x) {
     x = (x | (x << 2)) & 0x09249249u;
     return x;
 }
+// Particles outside [first_lo, first_hi) get the top key bit (free in both keys): a self call on a target shard sorts
+// its own particles to the front, so that target k is source k again (self_base = 0) and both parts are sorted.
 __global__ void direct_sort_keys(const double* __restrict__ pos, const double* __restrict__ h, int64_t n,
-                                 const double* __restrict__ bbox6, int by_position, uint32_t* __restrict__ key,
-                                 uint32_t* __restrict__ idx) {
+                                 const double* __restrict__ bbox6, int by_position, int64_t first_lo, int64_t first_hi,
+                                 uint32_t* __restrict__ key, uint32_t* __restrict__ idx) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     idx[i] = (uint32_t)i;
+    const uint32_t behind = (i < first_lo || i >= first_hi) ? 0x80000000u : 0u;
     if (!by_position) {
-        key[i] = __float_as_uint((float)fmax(h[i], 0.0));
+        key[i] = __float_as_uint((float)fmax(h[i], 0.0)) | behind;  // non-negative floats: sign bit free
         return;
     }
     uint32_t c[3];
@@ -943,7 +946,7 @@ __global__ void direct_sort_keys(const double* __restrict__ pos, const double* _
         u = fmin(fmax(u, 0.0), 1.0);
         c[d] = min(1023u, (uint32_t)(u * 1024.0));
     }
-    key[i] = spread10(c[0]) | (spread10(c[1]) << 1) | (spread10(c[2]) << 2);
+    key[i] = spread10(c[0]) | (spread10(c[1]) << 1) | (spread10(c[2]) << 2) | behind;  // 30-bit code
 }
 __global__ void gather_sorted(const uint32_t* __restrict__ perm, int64_t n, const double* __restrict__ pos,
                               const double* __restrict__ mass, const double* __restrict__ h, double* __restrict__ pos_s,
@@ -957,10 +960,10 @@ __global__ void gather_sorted(const uint32_t* __restrict__ perm, int64_t n, cons
 }
 // results of the sorted sweep back to the caller's order (also sums the source splits, in split order)
 __global__ void scatter_results(const uint32_t* __restrict__ perm, int64_t m, int splits, const double* __restrict__ pot_s,
-                                const double* __restrict__ acc_s, double* __restrict__ pot, double* __restrict__ acc) {
+                                const double* __restrict__ acc_s, int64_t first, double* __restrict__ pot, double* __restrict__ acc) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
-    const int64_t i = perm[k];
+    const int64_t i = (int64_t)perm[k] - first;  // slot in the caller's output: original index - tgt_begin
     if (pot) {
         double v = 0.0;
         for (int sidx = 0; sidx < splits; ++sidx) v += pot_s[(int64_t)sidx * m + k];
@@ -1200,7 +1203,8 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
 
     // ---- per-particle softenings: sort the particles so that whole (target block, source tile) combinations resolve
     // max(h_i, h_j) / "is any pair inside its softening radius" at once (TileMeta).
-    //   whole-array self calls: sources = targets, by softening for Plummer, along a Morton curve for the spline;
+    //   self calls: by softening for Plummer, along a Morton curve for the spline; the target shard's own particles
+    //     (all of them in a whole-array call) are sorted to the front, so target k is source k and self_base = 0;
     //   spline at points: the order of the sources is free, so they are Morton-sorted, and so are the points (inside
     //     the sources' bounding box) — Plummer at points needs no order (every tile takes its softening from the
     //     source records).
@@ -1209,15 +1213,16 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     const char* sort_env = getenv("PNBX_DIRECT_SORT_MIN");
     const int64_t sort_min = sort_env ? atoll(sort_env) : 65536;
     const bool can_sort = sizeof(T) == 4 && may_f2h && n >= sort_min && sort_min >= 0;
-    const bool sorted = can_sort && self && tgt_begin == 0 && m == n;           // sources and targets, one permutation
+    const bool sorted = can_sort && self;                                        // sources and targets, one permutation
     const bool sorted_pts = can_sort && !self && kernel == PNBX_KERNEL_SPLINE && m < ((int64_t)1 << 31);  // sources; points with their own
     DevBuf<uint32_t> perm;  // sorted target position -> caller's target index
     DevBuf<double> pos_s, mass_s, h_s, tgt_s;
-    auto sort_perm = [&](const double* p3, const double* hh, int64_t cnt, bool by_position, DevBuf<uint32_t>& out) {
+    auto sort_perm = [&](const double* p3, const double* hh, int64_t cnt, bool by_position, int64_t first_lo,
+                         int64_t first_hi, DevBuf<uint32_t>& out) {
         DevBuf<uint32_t> key((size_t)cnt, s), key_s((size_t)cnt, s), idx((size_t)cnt, s);
         out.alloc((size_t)cnt, s);
         PNBX_LAUNCH(direct_sort_keys, (unsigned)ceil_div(cnt, 256), 256, 0, s, p3, hh, cnt, bbox.get(), by_position ? 1 : 0,
-                    key.get(), idx.get());
+                    first_lo, first_hi, key.get(), idx.get());
         size_t bytes = 0;
         PNBX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key.get(), key_s.get(), idx.get(), out.get(), (int)cnt, 0, 32, s));
         DevBuf<uint8_t> tmp(bytes, s);
@@ -1227,7 +1232,8 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     if (sorted || sorted_pts) {
         DevBuf<uint32_t> sperm_own;
         DevBuf<uint32_t>& sperm = sorted ? perm : sperm_own;
-        sort_perm(d_pos, d_h, n, kernel == PNBX_KERNEL_SPLINE, sperm);
+        if (sorted) sort_perm(d_pos, d_h, n, kernel == PNBX_KERNEL_SPLINE, tgt_begin, tgt_begin + m, sperm);
+        else sort_perm(d_pos, d_h, n, true, 0, n, sperm);
         pos_s.alloc((size_t)3 * n, s);
         if (d_mass) mass_s.alloc((size_t)n, s);
         h_s.alloc((size_t)n, s);
@@ -1237,7 +1243,7 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
         if (d_mass) d_mass = mass_s.get();
         d_h = h_s.get();
         if (sorted_pts) {
-            sort_perm(d_tgt, nullptr, m, true, perm);
+            sort_perm(d_tgt, nullptr, m, true, 0, m, perm);
             tgt_s.alloc((size_t)3 * m, s);
             PNBX_LAUNCH(gather_sorted, (unsigned)ceil_div(m, 256), 256, 0, s, perm.get(), m, d_tgt, nullptr, nullptr, tgt_s.get(),
                         nullptr, nullptr);
@@ -1245,6 +1251,7 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
         }
     }
     const bool scatter_back = sorted || sorted_pts;
+    const int64_t tb = sorted ? 0 : tgt_begin;  // where the targets start in the (sorted) source arrays
 
     // ---- packing
     DevBuf<Vec4<T>> src4;
@@ -1277,7 +1284,7 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     }
     DevBuf<Vec4<T>> tgt4((size_t)m, s);
     {
-        const double* tp = self ? d_pos + 3 * tgt_begin : d_tgt;
+        const double* tp = self ? d_pos + 3 * tb : d_tgt;
         PNBX_LAUNCH(pack_points<T>, (unsigned)ceil_div(m, 256), 256, 0, s, tp, nullptr, m, bbox.get(), T(0), tgt4.get());
     }
     PNBX_CUDA(cudaGetLastError());
@@ -1302,7 +1309,7 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
     }
     tm.begin("direct.kernel");
     kernel_events().begin(s);
-    const int64_t sb = self ? tgt_begin : -1;
+    const int64_t sb = self ? tb : -1;
     dim3 grid((unsigned)n_tb, (unsigned)splits);
     if constexpr (sizeof(T) == 4) {
         const Pair8* sp = srcp.get();
@@ -1313,7 +1320,7 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
         if (may_f2_constm) PNBX_LAUNCH((direct_kernel_f2<W, true>), grid, DT, 0, s, sp, n, tp, m, sb, pl, tiles_per_split, kp, ka);  \
         if (may_f2) PNBX_LAUNCH((direct_kernel_f2<W, false>), grid, DT, 0, s, sp, n, tp, m, sb, pl, tiles_per_split, kp, ka);        \
         if (may_f2h) {                                                                                                 \
-            const float* th2 = self ? srch2.get() + tgt_begin : nullptr; /* at-points targets have no softening */    \
+            const float* th2 = self ? srch2.get() + tb : nullptr; /* at-points targets have no softening */           \
             const bool cm = may_f2_constm, gm = may_f2; /* equal / general masses: same host knowledge as for f2 */    \
             const TileMeta* tmp_ = tmeta.get();                                                                        \
             if (kernel == PNBX_KERNEL_PLUMMER) {                                                                       \
@@ -1333,14 +1340,14 @@ void run_direct(const Exec& ex, const double* d_pos, const double* d_mass, const
                                V_SCALAR_CONST, (int)splits, tiles_per_split, kp, ka, s);
     if (may_scalar_pair)
         launch_direct<T, TILE>(want, kernel == PNBX_KERNEL_SPLINE ? SOFT_SPLINE : SOFT_PLUMMER_PAIR, src4.get(), srch.get(), n,
-                               tgt4.get(), self ? srch.get() + tgt_begin : nullptr, m, sb, slot, V_SCALAR_PAIR,
+                               tgt4.get(), self ? srch.get() + tb : nullptr, m, sb, slot, V_SCALAR_PAIR,
                                (int)splits, tiles_per_split, kp, ka, s);
     release_plan_slot(ex.device, s, slot);
     kernel_events().end(s);
     PNBX_CUDA(cudaGetLastError());
     if (scatter_back) {
         PNBX_LAUNCH(scatter_results, (unsigned)ceil_div(m, 256), 256, 0, s, perm.get(), m, (int)splits,
-                    (want & PNBX_WANT_POT) ? kp : nullptr, (want & PNBX_WANT_ACC) ? ka : nullptr,
+                    (want & PNBX_WANT_POT) ? kp : nullptr, (want & PNBX_WANT_ACC) ? ka : nullptr, sorted ? tgt_begin : 0,
                     (want & PNBX_WANT_POT) ? d_pot : nullptr, (want & PNBX_WANT_ACC) ? d_acc : nullptr);
         PNBX_CUDA(cudaGetLastError());
     } else if (splits > 1) {

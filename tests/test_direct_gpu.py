@@ -296,3 +296,30 @@ def test_sorted_sweep_is_a_reordering_of_the_same_pair_terms(monkeypatch):
     assert np.array_equal(out["0"][2], out["-1"][2])
     monkeypatch.delenv("PNBX_DIRECT_SORT_MIN")  # default: sorted from 65536 particles
     assert np.array_equal(r.direct_accelerations_py(pos, m, 0, h, 1), out["0"][1])
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_self_shards_with_per_particle_softening_match_oracle(kernel):
+    # a self call on a target shard sorts the shard's own particles to the front of the source arrays (then target k
+    # is source k again: self-skip by index) and the rest behind them: every shard of the sum equals the oracle's
+    # slice, and the shards concatenate to the whole-array result to fp32 accumulation accuracy
+    import torch
+    from pynbodyext.gravity import device as gdev
+    n = 20_011
+    pos, m = hernquist(n, seed=31)
+    rng = np.random.default_rng(32)
+    h = rng.uniform(0.005, 0.05, n)
+    m = m * rng.uniform(0.5, 2.0, n)
+    p_o, a_o = O.direct(pos, m, h, kernel=kernel)
+    d = torch.device("cuda", 0)
+    dp, dm, dh = (torch.from_numpy(x).to(d) for x in (pos, m, h))
+    parts_p, parts_a = [], []
+    for lo, hi in ((0, 5000), (5000, 12_345), (12_345, n)):
+        p, a = gdev.direct_device(dp, dm, dh, kernel=kernel, want=3, tgt_begin=lo, count=hi - lo)
+        p, a = p.cpu().numpy(), a.cpu().numpy()
+        assert rms_rel(p, p_o[lo:hi]) < TOL32 and rms_rel_vec(a, a_o[lo:hi]) < TOL32
+        assert max_rel_vec(a, a_o[lo:hi]) < 2e-3
+        parts_p.append(p); parts_a.append(a)
+    p_w, a_w = gdev.direct_device(dp, dm, dh, kernel=kernel, want=3)
+    assert max_rel_vec(np.concatenate(parts_a), a_w.cpu().numpy()) < 1e-4
+    assert np.abs(np.concatenate(parts_p) / p_w.cpu().numpy() - 1).max() < 1e-5
