@@ -18,9 +18,9 @@ TOL64 = 1e-11
 
 @pytest.fixture(autouse=True, params=["caller_order", "sorted"])
 def direct_particle_order(request, monkeypatch):
-    """Whole-array self calls with per-particle softenings sort the particles (by softening for Plummer, along a Morton
-    curve for the spline) so that whole source tiles resolve max(h_i, h_j) / the r < h test at once; the default only
-    does so from 65536 particles (PNBX_DIRECT_SORT_MIN). Every test runs both ways."""
+    """Self calls with per-particle softenings (and spline sums at points) sort the particles — by softening for Plummer,
+    along a Morton curve for the spline — so that whole source tiles resolve max(h_i, h_j) / the r < h test at once;
+    the default only does so from 65536 particles (PNBX_DIRECT_SORT_MIN). Every test runs both ways."""
     monkeypatch.setenv("PNBX_DIRECT_SORT_MIN", "0" if request.param == "sorted" else "-1")
 
 
